@@ -41,41 +41,10 @@
 /* fp16 / bf16 conversion (IEEE binary16, round to nearest even)       */
 
 static inline float f16_to_f32(ggml_fp16_t h)
-{
-	uint32_t s = (uint32_t)(h & 0x8000) << 16, e = (h >> 10) & 0x1f, m = h & 0x3ff, u;
-	if (e == 0) {
-		if (m == 0) u = s;
-		else {
-			int sh = 0;
-			while (!(m & 0x400)) { m <<= 1; sh++; }
-			m &= 0x3ff;
-			u = s | ((uint32_t)(127 - 15 - sh + 1) << 23) | (m << 13);
-		}
-	}
-	else if (e == 31) u = s | 0x7f800000u | (m << 13);
-	else u = s | ((e + 127 - 15) << 23) | (m << 13);
-	float f; memcpy(&f, &u, 4); return f;
-}
+{ _Float16 x; memcpy(&x, &h, 2); return (float)x; }
 
 static inline ggml_fp16_t f32_to_f16(float f)
-{
-	uint32_t u; memcpy(&u, &f, 4);
-	uint32_t s = (u >> 16) & 0x8000, a = u & 0x7fffffffu;
-	if (a >= 0x7f800000u) return (ggml_fp16_t)(s | 0x7c00 | (a > 0x7f800000u ? 0x200 : 0));
-	if (a >= 0x477ff000u) return (ggml_fp16_t)(s | 0x7c00);  /* rounds to inf */
-	if (a < 0x38800000u) {  /* subnormal half or zero */
-		if (a < 0x33000000u) return (ggml_fp16_t)s;
-		int e = (int)(a >> 23);
-		uint32_t m = (a & 0x7fffff) | 0x800000;
-		int shift = 126 - e;  /* 14..24 */
-		uint32_t r = m >> shift, rem = m & ((1u << shift) - 1), half = 1u << (shift - 1);
-		if (rem > half || (rem == half && (r & 1))) r++;
-		return (ggml_fp16_t)(s | r);
-	}
-	uint32_t r = (a - 0x38000000u) >> 13, rem = a & 0x1fff;
-	if (rem > 0x1000 || (rem == 0x1000 && (r & 1))) r++;
-	return (ggml_fp16_t)(s | r);
-}
+{ _Float16 x = (_Float16)f; ggml_fp16_t h; memcpy(&h, &x, 2); return h; }
 
 static inline float f16_round(float f) { return f16_to_f32(f32_to_f16(f)); }
 
@@ -168,7 +137,7 @@ struct ggml_context* ggml_init(struct ggml_init_params p)
 void ggml_free(struct ggml_context* ctx)
 {
 	if (!ctx) return;
-	for (size_t i = 0; i < ctx->n; ++i) free(ctx->t[i]);
+	for (size_t i = 0; i < ctx->n; ++i) { free(ctx->t[i]->extra); free(ctx->t[i]); }
 	for (size_t i = 0; i < ctx->n_graphs; ++i) {
 		free(ctx->graphs[i]->nodes); free(ctx->graphs[i]->seen); free(ctx->graphs[i]);
 	}
@@ -596,6 +565,8 @@ void ggml_backend_tensor_set(struct ggml_tensor* t, const void* data, size_t off
 {
 	GGML_ASSERT(tensor_ptr(t) && off + size <= ggml_nbytes(t));
 	memcpy((char*)tensor_ptr(t) + off, data, size);
+	struct ggml_tensor* root = t->view_src ? t->view_src : t;
+	free(root->extra); root->extra = NULL;  /* drop the cached f32 copy */
 }
 void ggml_backend_tensor_get(const struct ggml_tensor* t, void* data, size_t off, size_t size)
 {
@@ -873,16 +844,26 @@ static void op_mul_mat(struct ggml_tensor* d)
 	bool round16 = a->type == GGML_TYPE_F16;
 	int64_t r2 = b->ne[2] / a->ne[2], r3 = b->ne[3] / a->ne[3];
 	float* af = NULL; int64_t af2 = -1, af3 = -1;
+	/* weights (2-d leaves) keep a cached f32 copy across computes */
+	bool a_leaf = a->op == GGML_OP_NONE && !a->view_src && a->ne[2] == 1 && a->ne[3] == 1;
 	for (int64_t i3 = 0; i3 < b->ne[3]; ++i3)
 	for (int64_t i2 = 0; i2 < b->ne[2]; ++i2) {
 		int64_t j2 = i2 / r2, j3 = i3 / r3;
-		if (j2 != af2 || j3 != af3) { free(af); af = rows_to_f32(a, pa, j2, j3, false); af2 = j2; af3 = j3; }
+		if (j2 != af2 || j3 != af3) {
+			if (!a_leaf) free(af);
+			if (a_leaf && a->extra) af = a->extra;
+			else {
+				af = rows_to_f32(a, pa, j2, j3, false);
+				if (a_leaf) ((struct ggml_tensor*)a)->extra = af;
+			}
+			af2 = j2; af3 = j3;
+		}
 		float* bf = rows_to_f32(b, pb, i2, i3, round16);
 		gemm_nt(a->ne[1], b->ne[1], a->ne[0], af, a->ne[0], bf, b->ne[0],
 			(float*)AT(d, pd, 0, 0, i2, i3), d->ne[0]);
 		free(bf);
 	}
-	free(af);
+	if (!a_leaf) free(af);
 }
 
 /* ggml_conv_2d(w,x,...) (mlblock_nn.c:44): im2col in the kernel's type (F16), then mul_mat;
@@ -898,9 +879,15 @@ static void op_conv_2d(struct ggml_tensor* d)
 	int64_t K = KW * KH * C;
 	bool round16 = w->type == GGML_TYPE_F16;
 	GGML_ASSERT(is_contiguous(w) && is_contiguous(d));
-	float* wf = malloc((size_t)K * OC * sizeof(float));
-	for (int64_t i = 0; i < K * OC; ++i)
-		wf[i] = w->type == GGML_TYPE_F16 ? f16_to_f32(((const ggml_fp16_t*)pw)[i]) : ((const float*)pw)[i];
+	bool w_leaf = w->op == GGML_OP_NONE && !w->view_src;
+	float* wf = w_leaf ? w->extra : NULL;
+	if (!wf) {
+		wf = malloc((size_t)K * OC * sizeof(float));
+		#pragma omp parallel for schedule(static)
+		for (int64_t i = 0; i < K * OC; ++i)
+			wf[i] = w->type == GGML_TYPE_F16 ? f16_to_f32(((const ggml_fp16_t*)pw)[i]) : ((const float*)pw)[i];
+		if (w_leaf) ((struct ggml_tensor*)w)->extra = wf;
+	}
 	float* col = malloc((size_t)OW * OH * K * sizeof(float) + 64);
 	float* out = malloc((size_t)OW * OH * OC * sizeof(float) + 64);
 	GGML_ASSERT(wf && col && out);
@@ -927,7 +914,8 @@ static void op_conv_2d(struct ggml_tensor* d)
 			for (int64_t i = 0; i < OW*OH; ++i)
 				pd[(n*OC + oc) * OW*OH + i] = out[i*OC + oc];
 	}
-	free(wf); free(col); free(out);
+	if (!w_leaf) free(wf);
+	free(col); free(out);
 }
 
 static void op_concat(struct ggml_tensor* d)
