@@ -1,0 +1,448 @@
+// gemm_tc.cu -- the tensor-core contraction kernel of the engine (sm_100a only).
+//
+// One kernel family serves every linear layer, 1x1 convolution and 3x3 convolution of the
+// UNet / VAE / CLIP / TAE graphs (reference emit sites: mlb_nn_linear mlblock_nn.c:16-28,
+// mlb_nn_conv2d mlblock_nn.c:31-55):
+//     C[M,N] = A[M,K] . B[N,K]^T   (f16 x f16 -> f32 accumulate, the reference's rounding points)
+//   * A (activations, rows = tokens/pixels, K contiguous) and B (weights, K contiguous) are staged
+//     by TMA (cp.async.bulk.tensor, 128B swizzle) into a multi-stage shared-memory ring;
+//   * a single elected thread issues tcgen05.mma (UMMA 128 x BN x 16, cta_group::1), accumulating
+//     in tensor memory (TMEM); tcgen05.commit releases ring slots / signals the epilogue;
+//   * four epilogue warps read the accumulator with tcgen05.ld and apply the fused epilogue:
+//     + bias[N], + per-image vector (the resnet time-embedding add, mlblock_nn.c:139-144),
+//     activation, + residual (mlblock_nn.c:154, unet.c:143), store f16/f32.
+//   * 3x3 stride-1 pad-1 convolution is an implicit GEMM: the A tile of tap (kh,kw) is a shifted
+//     4-D TMA box over the channels-last activation; out-of-bounds rows/cols are zero-filled by
+//     the TMA unit, which implements the padding. No im2col buffer exists.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+#include "kernels.h"
+#include <cuda.h>
+#include <algorithm>
+
+namespace b200 {
+
+constexpr int BM = 128;
+constexpr int BK = 64;            // 64 f16 = 128 B = one swizzle row
+constexpr int TMEM_COLS = 256;    // accumulator columns allocated per CTA (>= max BN)
+constexpr int MAX_STAGES = 8;
+
+struct GemmParams {
+	int M, N, K, num_kb, BN, stages;
+	int conv;                      // 0: plain GEMM, 1: implicit 3x3 s1 p1
+	int H, W, Cin, n_img, bw, bh, bi, tiles_w, tiles_h;
+	void* C; int c_dt; long long ldc;
+	const float* bias;
+	const void* rowvec; int rowvec_dt; long long rowvec_stride; long long rows_per_image;
+	const void* residual; int residual_dt; long long ldr;
+	int act;
+};
+
+struct GemmTC {
+	CUtensorMap tmA, tmB;
+	GemmParams p;
+	dim3 grid;
+	size_t smem;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+	uint32_t ok;
+	asm volatile("{\n\t.reg .pred p;\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+		"selp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+	return ok != 0;
+}
+// Bounded wait: a protocol bug must trap (reported as a launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+	if (mbar_try_wait(bar, parity)) return;
+	long long t0 = clock64();
+	while (!mbar_try_wait(bar, parity)) {
+		if (clock64() - t0 > 4000000000LL) {
+			printf("[ggml_b200] gemm_tc: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+			__trap();
+		}
+	}
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1)
+{
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+		:: "r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3)
+{
+	asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+		:: "r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm)
+{ asm volatile("prefetch.tensormap [%0];" :: "l"(tm) : "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols)
+{
+	asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+	asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols)
+{ asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(cols) : "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 (f16 inputs, f32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+		"tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+		:: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Arrive on an mbarrier once all previously issued MMAs have completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r)
+{
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+		: "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+		  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+		: "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row swizzle atoms 1024 B apart.
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
+//  layout SWIZZLE_128B=2 [61,64))
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr)
+{
+	return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// cute::UMMA::InstrDescriptor: c_format F32=1 [4,6), a/b format F16=0, K-major, N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24); }
+
+__device__ __forceinline__ float act_apply_tc(int op, float x)
+{
+	switch (op) {
+	case U_RELU: return fmaxf(x, 0.0f);
+	case U_SILU: return x / (1.0f + __expf(-x));
+	case U_GELU: { float u = 0.79788456080286535588f * x * (1.0f + 0.044715f * x * x); return 0.5f * x * (1.0f + tanhf(u)); }
+	case U_GELU_QUICK: return x / (1.0f + __expf(-1.702f * x));
+	case U_TANH: return tanhf(x);
+	default: return x;
+	}
+}
+
+// ------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p)
+{
+	extern __shared__ __align__(1024) uint8_t smem_raw[];
+	uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+	const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)p.BN * BK * 2, stage_bytes = a_bytes + b_bytes;
+	uint64_t* full_bar  = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
+	uint64_t* empty_bar = full_bar + MAX_STAGES;
+	uint64_t* accum_bar = empty_bar + MAX_STAGES;
+	uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int n0 = blockIdx.x * p.BN;
+	const int mt = blockIdx.y;
+	int m0 = mt * BM, tw0 = 0, th0 = 0, ti0 = 0;
+	if (p.conv) {
+		int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, ti = mt / (p.tiles_w * p.tiles_h);
+		tw0 = tw * p.bw; th0 = th * p.bh; ti0 = ti * p.bi;
+	}
+
+	if (threadIdx.x == 0) {
+		tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+		for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+		mbar_init(accum_bar, 1);
+		fence_barrier_init();
+	}
+	if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot;
+
+	if (warp == 0) {
+		// ===== TMA producer =====
+		if (lane == 0) {
+			const int cpt = p.conv ? p.Cin / BK : 1;  // channel chunks per tap
+			for (int kb = 0; kb < p.num_kb; ++kb) {
+				const int s = kb % p.stages;
+				const uint32_t ph = (uint32_t)(kb / p.stages) & 1;
+				mbar_wait(&empty_bar[s], ph ^ 1);
+				uint8_t* sa = smem + (size_t)s * stage_bytes;
+				uint8_t* sb = sa + a_bytes;
+				mbar_expect_tx(&full_bar[s], stage_bytes);
+				if (p.conv) {
+					const int tap = kb / cpt, cc = kb - tap * cpt;
+					const int kh = tap / 3, kw = tap - kh * 3;
+					tma_load_4d(sa, &tmA, &full_bar[s], cc * BK, tw0 + kw - 1, th0 + kh - 1, ti0);
+				} else {
+					tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m0);
+				}
+				tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n0);
+			}
+		}
+	} else if (warp == 1) {
+		// ===== MMA issuer (one thread) =====
+		if (lane == 0) {
+			const uint32_t idesc = make_idesc(p.BN);
+			for (int kb = 0; kb < p.num_kb; ++kb) {
+				const int s = kb % p.stages;
+				const uint32_t ph = (uint32_t)(kb / p.stages) & 1;
+				mbar_wait(&full_bar[s], ph);
+				tc_fence_after();
+				const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+				const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + a_bytes);
+				#pragma unroll
+				for (int k = 0; k < BK / 16; ++k) {
+					// advance 16 elements (32 B) along K inside the swizzle row: +2 in 16-byte units
+					umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+				}
+				umma_commit(&empty_bar[s]);          // slot reusable once these MMAs retire
+			}
+			umma_commit(accum_bar);                  // accumulator complete
+		}
+	} else {
+		// ===== epilogue warps 2..5 =====
+		const int quarter = warp & 3;                // TMEM lane quarter this warp may access
+		const int r = quarter * 32 + lane;           // row inside the tile
+		long long grow; bool row_ok;
+		if (p.conv) {
+			int wi = r % p.bw, hi = (r / p.bw) % p.bh, ii = r / (p.bw * p.bh);
+			int w = tw0 + wi, h = th0 + hi, im = ti0 + ii;
+			row_ok = w < p.W && h < p.H && im < p.n_img;
+			grow = ((long long)im * p.H + h) * p.W + w;
+		} else {
+			grow = (long long)m0 + r;
+			row_ok = grow < p.M;
+		}
+		const long long img = p.rowvec ? grow / p.rows_per_image : 0;
+		mbar_wait(accum_bar, 0);
+		tc_fence_after();
+		const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+		for (int c0 = 0; c0 < p.BN; c0 += 16) {
+			uint32_t v[16];
+			tmem_ld16(trow + (uint32_t)c0, v);
+			tmem_ld_wait();
+			const int col0 = n0 + c0;
+			if (!row_ok || col0 >= p.N) continue;
+			float f[16];
+			#pragma unroll
+			for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+			const bool full = col0 + 16 <= p.N;
+			if (p.bias) {
+				#pragma unroll
+				for (int j = 0; j < 16; ++j) if (full || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+			}
+			if (p.rowvec) {
+				#pragma unroll
+				for (int j = 0; j < 16; ++j) if (full || col0 + j < p.N) {
+					long long o = img * p.rowvec_stride + col0 + j;
+					f[j] += p.rowvec_dt == DT_F16 ? __half2float(((const __half*)p.rowvec)[o]) : ((const float*)p.rowvec)[o];
+				}
+			}
+			if (p.act != U_NONE) {
+				#pragma unroll
+				for (int j = 0; j < 16; ++j) f[j] = act_apply_tc(p.act, f[j]);
+			}
+			if (p.residual) {
+				const long long ro = grow * p.ldr + col0;
+				if (p.residual_dt == DT_F16) {
+					const __half* rp = (const __half*)p.residual + ro;
+					if (full && ((ro & 7) == 0)) {
+						uint4 a = *reinterpret_cast<const uint4*>(rp), b = *reinterpret_cast<const uint4*>(rp + 8);
+						const __half2* ha = reinterpret_cast<const __half2*>(&a); const __half2* hb = reinterpret_cast<const __half2*>(&b);
+						#pragma unroll
+						for (int j = 0; j < 4; ++j) { float2 x = __half22float2(ha[j]), y = __half22float2(hb[j]);
+							f[2*j] += x.x; f[2*j+1] += x.y; f[8+2*j] += y.x; f[8+2*j+1] += y.y; }
+					} else {
+						#pragma unroll
+						for (int j = 0; j < 16; ++j) if (full || col0 + j < p.N) f[j] += __half2float(rp[j]);
+					}
+				} else {
+					const float* rp = (const float*)p.residual + ro;
+					#pragma unroll
+					for (int j = 0; j < 16; ++j) if (full || col0 + j < p.N) f[j] += rp[j];
+				}
+			}
+			const long long co = grow * p.ldc + col0;
+			if (p.c_dt == DT_F16) {
+				__half* cp = (__half*)p.C + co;
+				if (full && ((co & 7) == 0)) {
+					uint4 a, b; __half2* ha = reinterpret_cast<__half2*>(&a); __half2* hb = reinterpret_cast<__half2*>(&b);
+					#pragma unroll
+					for (int j = 0; j < 4; ++j) { ha[j] = __floats2half2_rn(f[2*j], f[2*j+1]); hb[j] = __floats2half2_rn(f[8+2*j], f[8+2*j+1]); }
+					*reinterpret_cast<uint4*>(cp) = a; *reinterpret_cast<uint4*>(cp + 8) = b;
+				} else {
+					#pragma unroll
+					for (int j = 0; j < 16; ++j) if (full || col0 + j < p.N) cp[j] = __float2half_rn(f[j]);
+				}
+			} else {
+				float* cp = (float*)p.C + co;
+				if (full && ((co & 3) == 0)) {
+					#pragma unroll
+					for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(cp + 4 * j) = make_float4(f[4*j], f[4*j+1], f[4*j+2], f[4*j+3]);
+				} else {
+					#pragma unroll
+					for (int j = 0; j < 16; ++j) if (full || col0 + j < p.N) cp[j] = f[j];
+				}
+			}
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+	const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode()
+{
+	static PFN_encodeTiled fn = nullptr;
+	if (!fn) {
+		void* p = nullptr; cudaDriverEntryPointQueryResult qres;
+		CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+		if (!p || qres != cudaDriverEntryPointSuccess) B200_FATAL("cuTensorMapEncodeTiled not available in this driver");
+		fn = (PFN_encodeTiled)p;
+	}
+	return fn;
+}
+
+static void encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+	const cuuint32_t* box)
+{
+	cuuint32_t es[5] = {1, 1, 1, 1, 1};
+	CUresult r = get_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+		box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+		CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) {
+		B200_FATAL("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu %llu box %u %u %u %u base %p stride0 %llu", (int)r, rank,
+			(unsigned long long)dims[0], (unsigned long long)dims[1], rank > 2 ? (unsigned long long)dims[2] : 0ull, rank > 3 ? (unsigned long long)dims[3] : 0ull,
+			box[0], box[1], rank > 2 ? box[2] : 0u, rank > 3 ? box[3] : 0u, base, (unsigned long long)strides_bytes[0]);
+	}
+}
+
+bool gemm_tc_supported(int64_t M, int64_t N, int64_t K)
+{
+	return M >= 1 && N >= 1 && K >= 8 && (K % 8) == 0;
+}
+
+// Pick the N tile: minimise (waves x per-tile time), per-tile time ~ BN + fixed overhead.
+static int pick_bn(int64_t m_tiles, int64_t N, int sm_count)
+{
+	int best = 64; double best_cost = 1e30;
+	for (int bn = 256; bn >= 16; bn -= 16) {
+		if (bn > 16 && bn - 16 >= N) continue;   // no point in a tile much wider than N
+		int64_t nt = (N + bn - 1) / bn, tiles = nt * m_tiles;
+		int64_t waves = (tiles + sm_count - 1) / sm_count;
+		double cost = (double)waves * (bn + 40.0);
+		if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+	}
+	return best;
+}
+
+static void finish_setup(GemmTC* g, const GemmEpilogue& ep, int64_t m_tiles, int sm_count)
+{
+	GemmParams& p = g->p;
+	p.BN = pick_bn(m_tiles, p.N, sm_count);
+	size_t stage = (size_t)BM * BK * 2 + (size_t)p.BN * BK * 2;
+	int stages = (int)std::min<size_t>(MAX_STAGES, (200 * 1024) / stage);
+	stages = std::max(2, std::min(stages, std::max(2, p.num_kb)));
+	p.stages = stages;
+	g->smem = stages * stage + 1024 /*align*/ + (2 * MAX_STAGES + 1) * 8 + 16;
+	g->grid = dim3((unsigned)((p.N + p.BN - 1) / p.BN), (unsigned)m_tiles);
+	p.bias = ep.bias; p.rowvec = ep.rowvec; p.rowvec_dt = ep.rowvec_dt; p.rowvec_stride = ep.rowvec_stride;
+	p.rows_per_image = ep.rows_per_image > 0 ? ep.rows_per_image : 1;
+	p.residual = ep.residual; p.residual_dt = ep.residual_dt; p.ldr = ep.ldr; p.act = ep.act;
+}
+
+GemmTC* gemm_tc_prepare(const __half* A, int64_t lda, const __half* B, int64_t ldb,
+	void* C, DT c_dt, int64_t ldc, int64_t M, int64_t N, int64_t K, const GemmEpilogue& ep, int sm_count)
+{
+	if (!gemm_tc_supported(M, N, K) || (lda % 8) || (ldb % 8) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15))
+		B200_FATAL("gemm_tc_prepare: unsupported operands M=%lld N=%lld K=%lld lda=%lld ldb=%lld", (long long)M, (long long)N, (long long)K, (long long)lda, (long long)ldb);
+	GemmTC* g = new GemmTC();
+	GemmParams& p = g->p;
+	memset(&p, 0, sizeof(p));
+	p.M = (int)M; p.N = (int)N; p.K = (int)K; p.num_kb = (int)((K + BK - 1) / BK);
+	p.C = C; p.c_dt = c_dt; p.ldc = ldc;
+	int64_t m_tiles = (M + BM - 1) / BM;
+	finish_setup(g, ep, m_tiles, sm_count);
+	cuuint64_t da[2] = { (cuuint64_t)K, (cuuint64_t)M }, sa[1] = { (cuuint64_t)lda * 2 };
+	cuuint32_t ba[2] = { BK, BM };
+	encode_map(&g->tmA, A, 2, da, sa, ba);
+	cuuint64_t db[2] = { (cuuint64_t)K, (cuuint64_t)N }, sb[1] = { (cuuint64_t)ldb * 2 };
+	cuuint32_t bb[2] = { BK, (cuuint32_t)p.BN };
+	encode_map(&g->tmB, B, 2, db, sb, bb);
+	return g;
+}
+
+static int pow2_le(int64_t x, int cap) { int r = 1; while (r * 2 <= x && r * 2 <= cap) r *= 2; return r; }
+// Tile extent along one image axis: the largest power of two that divides n (no wasted rows);
+// if that is tiny compared to n, accept a partial last tile instead.
+static int tile_extent(int64_t n, int cap)
+{
+	int d = 1; while (d * 2 <= cap && n % (d * 2) == 0) d *= 2;
+	int le = pow2_le(n, cap);
+	return (d >= 8 || d == le) ? d : le;
+}
+
+GemmTC* conv3x3_tc_prepare(const __half* x, int64_t n_img, int64_t H, int64_t W, int64_t Cin,
+	const __half* Wt, void* C, DT c_dt, int64_t Cout, const GemmEpilogue& ep, int sm_count)
+{
+	if (Cin % BK || ((uintptr_t)x & 15) || ((uintptr_t)Wt & 15))
+		B200_FATAL("conv3x3_tc_prepare: Cin=%lld must be a multiple of %d", (long long)Cin, BK);
+	GemmTC* g = new GemmTC();
+	GemmParams& p = g->p;
+	memset(&p, 0, sizeof(p));
+	p.conv = 1; p.H = (int)H; p.W = (int)W; p.Cin = (int)Cin; p.n_img = (int)n_img;
+	p.M = (int)(n_img * H * W); p.N = (int)Cout; p.K = (int)(9 * Cin); p.num_kb = (int)(9 * Cin / BK);
+	p.C = C; p.c_dt = c_dt; p.ldc = Cout;
+	// 128 output pixels per tile = bw x bh x bi (columns x rows x images), powers of two
+	p.bw = tile_extent(W, BM);
+	p.bh = tile_extent(H, BM / p.bw);
+	p.bi = BM / (p.bw * p.bh);
+	p.tiles_w = (int)((W + p.bw - 1) / p.bw);
+	p.tiles_h = (int)((H + p.bh - 1) / p.bh);
+	int64_t tiles_i = (n_img + p.bi - 1) / p.bi;
+	int64_t m_tiles = (int64_t)p.tiles_w * p.tiles_h * tiles_i;
+	finish_setup(g, ep, m_tiles, sm_count);
+	cuuint64_t da[4] = { (cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img };
+	cuuint64_t sa[3] = { (cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2 };
+	cuuint32_t ba[4] = { BK, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bi };
+	encode_map(&g->tmA, x, 4, da, sa, ba);
+	cuuint64_t db[2] = { (cuuint64_t)(9 * Cin), (cuuint64_t)Cout }, sb[1] = { (cuuint64_t)(9 * Cin) * 2 };
+	cuuint32_t bb[2] = { BK, (cuuint32_t)p.BN };
+	encode_map(&g->tmB, Wt, 2, db, sb, bb);
+	return g;
+}
+
+void gemm_tc_launch(cudaStream_t s, GemmTC* g)
+{
+	static bool attr_set = false;
+	if (!attr_set) {
+		CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		attr_set = true;
+	}
+	gemm_tc_kernel<<<g->grid, 192, g->smem, s>>>(g->tmA, g->tmB, g->p);
+	g_stats.kernel_launches++;
+}
+
+void gemm_tc_free(GemmTC* g) { delete g; }
+
+}  // namespace b200

@@ -1,0 +1,553 @@
+// kernels_elem.cu -- generic strided kernels and the fused memory-bound kernels
+// (GroupNorm+SiLU, LayerNorm, GEGLU gate, im2col, weight prep) of the B200 engine.
+// Rooflines: everything in this file is HBM/L2-bandwidth bound; the hot ones are vectorised
+// to 16-byte accesses with channels innermost so that a warp touches contiguous 512 B.
+#include "kernels.h"
+#include <algorithm>
+
+namespace b200 {
+
+// ------------------------------------------------------------------ helpers
+struct V4 {               // device copy of a View with an iteration order
+	void* ptr; int dt;
+	long long ne[4], st[4];
+};
+struct Iter4 { long long n[4]; int ord[4]; long long total; };
+
+static V4 v4(const View& v) { V4 r; r.ptr = v.ptr; r.dt = v.dt; for (int i = 0; i < 4; ++i) { r.ne[i] = v.ne[i]; r.st[i] = v.st[i]; } return r; }
+
+// Iterate dst in order of increasing dst stride so consecutive threads write consecutive memory.
+static Iter4 iter_for(const View& dst)
+{
+	Iter4 it;
+	int ord[4] = {0, 1, 2, 3};
+	std::stable_sort(ord, ord + 4, [&](int a, int b) {
+		long long sa = dst.ne[a] == 1 ? (1LL << 60) : dst.st[a], sb = dst.ne[b] == 1 ? (1LL << 60) : dst.st[b];
+		return sa < sb; });
+	it.total = 1;
+	for (int i = 0; i < 4; ++i) { it.ord[i] = ord[i]; it.n[i] = dst.ne[ord[i]]; it.total *= it.n[i]; }
+	return it;
+}
+
+__device__ __forceinline__ void decompose(const Iter4& it, long long lin, long long idx[4])
+{
+	#pragma unroll
+	for (int i = 0; i < 4; ++i) { long long n = it.n[i]; long long q = lin / n; idx[it.ord[i]] = lin - q * n; lin = q; }
+}
+__device__ __forceinline__ float ldv(const V4& v, long long off)
+{
+	if (v.dt == DT_F16) return __half2float(((const __half*)v.ptr)[off]);
+	if (v.dt == DT_I32) return (float)((const int*)v.ptr)[off];
+	return ((const float*)v.ptr)[off];
+}
+__device__ __forceinline__ void stv(const V4& v, long long off, float x)
+{
+	if (v.dt == DT_F16) ((__half*)v.ptr)[off] = __float2half_rn(x);
+	else if (v.dt == DT_I32) ((int*)v.ptr)[off] = (int)x;
+	else ((float*)v.ptr)[off] = x;
+}
+__device__ __forceinline__ long long offs(const V4& v, const long long i[4])
+{ return i[0] * v.st[0] + i[1] * v.st[1] + i[2] * v.st[2] + i[3] * v.st[3]; }
+
+static inline int grid_for(long long total, int block, long long per_thread = 1)
+{
+	long long g = (total + (long long)block * per_thread - 1) / ((long long)block * per_thread);
+	return (int)std::min<long long>(std::max<long long>(g, 1), 148LL * 32);
+}
+
+__device__ __forceinline__ float act_apply(int op, float x, float p)
+{
+	switch (op) {
+	case U_TANH: return tanhf(x);
+	case U_RELU: return fmaxf(x, 0.0f);
+	case U_SILU: return x / (1.0f + __expf(-x));
+	case U_GELU: {  // tanh approximation, as the reference's ggml_gelu
+		float u = 0.79788456080286535588f * x * (1.0f + 0.044715f * x * x);
+		return 0.5f * x * (1.0f + tanhf(u));
+	}
+	case U_GELU_QUICK: return x / (1.0f + __expf(-1.702f * x));
+	case U_SCALE: return x * p;
+	default: return x;
+	}
+}
+
+// ------------------------------------------------------------------ copy / convert
+__global__ void copy_kernel(V4 dst, V4 src, Iter4 it)
+{
+	for (long long lin = blockIdx.x * (long long)blockDim.x + threadIdx.x; lin < it.total;
+	     lin += (long long)gridDim.x * blockDim.x) {
+		long long i[4]; decompose(it, lin, i);
+		if (dst.dt == DT_I32 && src.dt == DT_I32) ((int*)dst.ptr)[offs(dst, i)] = ((const int*)src.ptr)[offs(src, i)];
+		else stv(dst, offs(dst, i), ldv(src, offs(src, i)));
+	}
+}
+void k_copy(cudaStream_t s, const View& dst, const View& src)
+{
+	Iter4 it = iter_for(dst);
+	if (!it.total) return;
+	copy_kernel<<<grid_for(it.total, 256), 256, 0, s>>>(v4(dst), v4(src), it);
+	g_stats.kernel_launches++;
+}
+
+// ------------------------------------------------------------------ binary with broadcast
+__global__ void binary_kernel(int op, V4 dst, V4 a, V4 b, Iter4 it)
+{
+	for (long long lin = blockIdx.x * (long long)blockDim.x + threadIdx.x; lin < it.total;
+	     lin += (long long)gridDim.x * blockDim.x) {
+		long long i[4], j[4]; decompose(it, lin, i);
+		#pragma unroll
+		for (int d = 0; d < 4; ++d) j[d] = b.ne[d] == 1 ? 0 : (i[d] % b.ne[d]);
+		float x = ldv(a, offs(a, i)), y = ldv(b, offs(b, j));
+		stv(dst, offs(dst, i), op == B_MUL ? x * y : x + y);
+	}
+}
+void k_binary(cudaStream_t s, BinOp op, const View& dst, const View& a, const View& b)
+{
+	Iter4 it = iter_for(dst);
+	if (!it.total) return;
+	binary_kernel<<<grid_for(it.total, 256), 256, 0, s>>>((int)op, v4(dst), v4(a), v4(b), it);
+	g_stats.kernel_launches++;
+}
+
+// ------------------------------------------------------------------ unary / scale
+__global__ void unary_kernel(int op, float p, V4 dst, V4 src, Iter4 it)
+{
+	for (long long lin = blockIdx.x * (long long)blockDim.x + threadIdx.x; lin < it.total;
+	     lin += (long long)gridDim.x * blockDim.x) {
+		long long i[4]; decompose(it, lin, i);
+		stv(dst, offs(dst, i), act_apply(op, ldv(src, offs(src, i)), p));
+	}
+}
+void k_unary(cudaStream_t s, UnaryOp op, float param, const View& dst, const View& src)
+{
+	Iter4 it = iter_for(dst);
+	if (!it.total) return;
+	unary_kernel<<<grid_for(it.total, 256), 256, 0, s>>>((int)op, param, v4(dst), v4(src), it);
+	g_stats.kernel_launches++;
+}
+
+// ------------------------------------------------------------------ nearest upscale (mlblock_nn.c:122)
+__global__ void upscale_kernel(V4 dst, V4 src, Iter4 it, int f0, int f1)
+{
+	for (long long lin = blockIdx.x * (long long)blockDim.x + threadIdx.x; lin < it.total;
+	     lin += (long long)gridDim.x * blockDim.x) {
+		long long i[4]; decompose(it, lin, i);
+		long long j[4] = { i[0] / f0, i[1] / f1, i[2], i[3] };
+		stv(dst, offs(dst, i), ldv(src, offs(src, j)));
+	}
+}
+void k_upscale(cudaStream_t s, const View& dst, const View& src)
+{
+	Iter4 it = iter_for(dst);
+	upscale_kernel<<<grid_for(it.total, 256), 256, 0, s>>>(v4(dst), v4(src), it,
+		(int)(dst.ne[0] / src.ne[0]), (int)(dst.ne[1] / src.ne[1]));
+	g_stats.kernel_launches++;
+}
+
+// ------------------------------------------------------------------ softmax over dim 0 (generic fallback)
+__global__ void softmax_rows_kernel(V4 dst, V4 src, int causal, int n_past)
+{
+	long long row = blockIdx.x;
+	long long i1 = row % src.ne[1], i2 = (row / src.ne[1]) % src.ne[2], i3 = row / (src.ne[1] * src.ne[2]);
+	long long so = i1 * src.st[1] + i2 * src.st[2] + i3 * src.st[3];
+	long long dof = i1 * dst.st[1] + i2 * dst.st[2] + i3 * dst.st[3];
+	long long n = src.ne[0];
+	long long lim = causal ? min(n, (long long)n_past + i1 + 1) : n;
+	__shared__ float red[32];
+	float mx = -INFINITY;
+	for (long long i = threadIdx.x; i < lim; i += blockDim.x) mx = fmaxf(mx, ldv(src, so + i * src.st[0]));
+	for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(~0u, mx, o));
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+	__syncthreads();
+	mx = red[0];
+	for (int w = 1; w < (blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+	__syncthreads();
+	float sum = 0;
+	for (long long i = threadIdx.x; i < lim; i += blockDim.x) sum += __expf(ldv(src, so + i * src.st[0]) - mx);
+	for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(~0u, sum, o);
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+	__syncthreads();
+	sum = 0;
+	for (int w = 0; w < (blockDim.x >> 5); ++w) sum += red[w];
+	float inv = 1.0f / sum;
+	for (long long i = threadIdx.x; i < n; i += blockDim.x)
+		stv(dst, dof + i * dst.st[0], i < lim ? __expf(ldv(src, so + i * src.st[0]) - mx) * inv : 0.0f);
+}
+void k_softmax_rows(cudaStream_t s, const View& dst, const View& src, bool causal, int n_past)
+{
+	long long rows = src.ne[1] * src.ne[2] * src.ne[3];
+	softmax_rows_kernel<<<(unsigned)rows, 128, 0, s>>>(v4(dst), v4(src), causal ? 1 : 0, n_past);
+	g_stats.kernel_launches++;
+}
+
+// ------------------------------------------------------------------ get_rows (clip.c:338)
+__global__ void get_rows_kernel(V4 dst, V4 table, V4 ids)
+{
+	long long r = blockIdx.x;  // over dst rows (i1,i2,i3)
+	long long i1 = r % dst.ne[1], i2 = (r / dst.ne[1]) % dst.ne[2], i3 = r / (dst.ne[1] * dst.ne[2]);
+	int row = ((const int*)ids.ptr)[i1 * ids.st[0] + i2 * ids.st[1] + i3 * ids.st[2]];
+	row = max(0, min(row, (int)table.ne[1] - 1));
+	for (long long i0 = threadIdx.x; i0 < dst.ne[0]; i0 += blockDim.x)
+		stv(dst, i0 * dst.st[0] + i1 * dst.st[1] + i2 * dst.st[2] + i3 * dst.st[3],
+			ldv(table, i0 * table.st[0] + row * table.st[1] + i2 * table.st[2]));
+}
+void k_get_rows(cudaStream_t s, const View& dst, const View& table, const View& ids)
+{
+	get_rows_kernel<<<(unsigned)(dst.ne[1] * dst.ne[2] * dst.ne[3]), 128, 0, s>>>(v4(dst), v4(table), v4(ids));
+	g_stats.kernel_launches++;
+}
+
+// ------------------------------------------------------------------ timestep embedding (unet.c:150): cos first
+__global__ void timestep_embedding_kernel(V4 dst, V4 ts, int dim, int max_period)
+{
+	int half = dim / 2;
+	long long i = blockIdx.x;
+	float t = ldv(ts, i * ts.st[0]);
+	for (int j = threadIdx.x; j < half; j += blockDim.x) {
+		float freq = expf(-logf((float)max_period) * j / half);
+		float arg = t * freq;
+		stv(dst, i * dst.st[1] + j * dst.st[0], cosf(arg));
+		stv(dst, i * dst.st[1] + (j + half) * dst.st[0], sinf(arg));
+	}
+	if ((dim & 1) && threadIdx.x == 0) stv(dst, i * dst.st[1] + dim * dst.st[0], 0.0f);
+}
+void k_timestep_embedding(cudaStream_t s, const View& dst, const View& ts, int dim, int max_period)
+{
+	timestep_embedding_kernel<<<(unsigned)ts.ne[0], 128, 0, s>>>(v4(dst), v4(ts), dim, max_period);
+	g_stats.kernel_launches++;
+}
+
+// ------------------------------------------------------------------ generic SIMT GEMM (fallback / debug reference)
+// c[m,n,b2,b3] = sum_k a[k,m,b2/r2,b3/r3] * b[k,n,b2,b3]; 32x32 tiles, K step 16.
+__global__ void gemm_simt_kernel(V4 c, V4 a, V4 b, int round_b)
+{
+	__shared__ float sa[16][33], sb[16][33];
+	long long M = a.ne[1], N = b.ne[1], K = a.ne[0];
+	long long bz = blockIdx.z, i2 = bz % b.ne[2], i3 = bz / b.ne[2];
+	long long a2 = i2 / (b.ne[2] / a.ne[2]), a3 = i3 / (b.ne[3] / a.ne[3]);
+	long long m0 = blockIdx.x * 32LL, n0 = blockIdx.y * 32LL;
+	int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+	float acc[4] = {0, 0, 0, 0};
+	for (long long k0 = 0; k0 < K; k0 += 16) {
+		for (int e = ty * 32 + tx; e < 16 * 32; e += 256) {
+			int kk = e & 15, r = e >> 4;
+			long long k = k0 + kk;
+			float va = 0, vb = 0;
+			if (k < K && m0 + r < M) va = ldv(a, k * a.st[0] + (m0 + r) * a.st[1] + a2 * a.st[2] + a3 * a.st[3]);
+			if (k < K && n0 + r < N) {
+				vb = ldv(b, k * b.st[0] + (n0 + r) * b.st[1] + i2 * b.st[2] + i3 * b.st[3]);
+				if (round_b) vb = __half2float(__float2half_rn(vb));
+			}
+			sa[kk][r] = va; sb[kk][r] = vb;
+		}
+		__syncthreads();
+		#pragma unroll
+		for (int kk = 0; kk < 16; ++kk) {
+			float x = sa[kk][tx];
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) acc[j] += x * sb[kk][ty * 4 + j];
+		}
+		__syncthreads();
+	}
+	for (int j = 0; j < 4; ++j) {
+		long long m = m0 + tx, n = n0 + ty * 4 + j;
+		if (m < M && n < N) stv(c, m * c.st[0] + n * c.st[1] + i2 * c.st[2] + i3 * c.st[3], acc[j]);
+	}
+}
+void k_gemm_simt(cudaStream_t s, const View& c, const View& a, const View& b, bool round_b_f16)
+{
+	dim3 grid((unsigned)((a.ne[1] + 31) / 32), (unsigned)((b.ne[1] + 31) / 32), (unsigned)(b.ne[2] * b.ne[3]));
+	gemm_simt_kernel<<<grid, dim3(32, 8), 0, s>>>(v4(c), v4(a), v4(b), round_b_f16 ? 1 : 0);
+	g_stats.kernel_launches++;
+}
+
+// ------------------------------------------------------------------ GroupNorm (+affine, +SiLU), channels-last f16
+// (mlblock_nn.c:78-103 + ggml_silu_inplace :136,147). Reference statistics are double sums; here
+// per-thread f32 partials over <= 64 elements are combined in double.
+// Pass 1: block = 256 threads covers a tile of pixels x all channels (coalesced), per-group partial
+// sums in shared memory, one double atomicAdd pair per group per block.
+template <typename T>
+__global__ void gn_stats_kernel(const T* __restrict__ x, long long HW, int C, int cpg, int groups,
+	long long img_stride, long long pix_stride, double* __restrict__ stats, int pix_per_block)
+{
+	extern __shared__ float sm[];  // [groups][2]
+	int n = blockIdx.y;
+	for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sm[i] = 0.f;
+	__syncthreads();
+	long long p0 = (long long)blockIdx.x * pix_per_block;
+	long long np = min(HW - p0, (long long)pix_per_block);
+	const T* base = x + n * img_stride + p0 * pix_stride;
+	int chunks = C / 8;
+	long long items = np * chunks;
+	for (long long it = threadIdx.x; it < items; it += blockDim.x) {
+		long long p = it / chunks; int ch = (int)(it - p * chunks);
+		const T* ptr = base + p * pix_stride + ch * 8;
+		float v[8];
+		if (sizeof(T) == 2) {
+			uint4 raw = *reinterpret_cast<const uint4*>(ptr);
+			const __half2* h = reinterpret_cast<const __half2*>(&raw);
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) { float2 f = __half22float2(h[j]); v[2*j] = f.x; v[2*j+1] = f.y; }
+		} else {
+			#pragma unroll
+			for (int j = 0; j < 8; ++j) v[j] = (float)ptr[j];
+		}
+		// run-length combine channels of the same group before touching shared memory
+		int g = (ch * 8) / cpg;
+		float su = 0.f, sq = 0.f;
+		#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			int gj = (ch * 8 + j) / cpg;
+			if (gj != g) { atomicAdd(&sm[g * 2], su); atomicAdd(&sm[g * 2 + 1], sq); su = 0.f; sq = 0.f; g = gj; }
+			su += v[j]; sq += v[j] * v[j];
+		}
+		atomicAdd(&sm[g * 2], su); atomicAdd(&sm[g * 2 + 1], sq);
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < groups * 2; i += blockDim.x)
+		atomicAdd(&stats[(long long)n * groups * 2 + i], (double)sm[i]);
+}
+
+template <typename TI, typename TO>
+__global__ void gn_apply_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long HW, int C, int cpg, int groups,
+	long long img_stride, long long pix_stride, long long oimg_stride, long long opix_stride,
+	const float* __restrict__ gamma, const float* __restrict__ beta, const double* __restrict__ stats,
+	float eps, int silu)
+{
+	extern __shared__ float sm[];  // mean[groups], rstd[groups]
+	int n = blockIdx.y;
+	double cnt = (double)HW * cpg;
+	for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+		double su = stats[((long long)n * groups + g) * 2], sq = stats[((long long)n * groups + g) * 2 + 1];
+		double mean = su / cnt, var = sq / cnt - mean * mean;
+		if (var < 0) var = 0;
+		sm[g] = (float)mean;
+		sm[groups + g] = (float)(1.0 / sqrt(var + (double)eps));
+	}
+	__syncthreads();
+	int chunks = C / 8;
+	long long total = HW * chunks;
+	for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+		long long p = e / chunks; int ch = (int)(e - p * chunks);
+		const TI* ptr = x + n * img_stride + p * pix_stride + ch * 8;
+		float v[8];
+		if (sizeof(TI) == 2) {
+			uint4 raw = *reinterpret_cast<const uint4*>(ptr);
+			const __half2* h = reinterpret_cast<const __half2*>(&raw);
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) { float2 f = __half22float2(h[j]); v[2*j] = f.x; v[2*j+1] = f.y; }
+		} else {
+			#pragma unroll
+			for (int j = 0; j < 8; ++j) v[j] = (float)ptr[j];
+		}
+		#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			int c = ch * 8 + j, g = c / cpg;
+			float t = (v[j] - sm[g]) * sm[groups + g];
+			if (gamma) t = t * gamma[c] + (beta ? beta[c] : 0.f);
+			if (silu) t = t / (1.0f + __expf(-t));
+			v[j] = t;
+		}
+		TO* optr = y + n * oimg_stride + p * opix_stride + ch * 8;
+		if (sizeof(TO) == 2) {
+			uint4 raw; __half2* h = reinterpret_cast<__half2*>(&raw);
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[2*j], v[2*j+1]);
+			*reinterpret_cast<uint4*>(optr) = raw;
+		} else {
+			#pragma unroll
+			for (int j = 0; j < 8; ++j) optr[j] = (TO)v[j];
+		}
+	}
+}
+
+void k_groupnorm(cudaStream_t s, const View& dst, const View& src, const float* gamma, const float* beta,
+	int groups, float eps, bool silu, double* stats)
+{
+	int C = (int)src.ne[2]; long long W = src.ne[0], H = src.ne[1], N = src.ne[3], HW = W * H;
+	int cpg = (C + groups - 1) / groups;
+	if (src.st[2] != 1 || dst.st[2] != 1 || C % 8 || src.st[1] != W * src.st[0] || dst.st[1] != W * dst.st[0])
+		B200_FATAL("k_groupnorm: unsupported layout (C=%d)", C);
+	int threads = 256;
+	int pix_per_block = 64;
+	dim3 g1((unsigned)((HW + pix_per_block - 1) / pix_per_block), (unsigned)N);
+	size_t smem = groups * 2 * sizeof(float);
+	if (src.dt == DT_F16)
+		gn_stats_kernel<__half><<<g1, threads, smem, s>>>((const __half*)src.ptr, HW, C, cpg, groups, src.st[3], src.st[0], stats, pix_per_block);
+	else
+		gn_stats_kernel<float><<<g1, threads, smem, s>>>((const float*)src.ptr, HW, C, cpg, groups, src.st[3], src.st[0], stats, pix_per_block);
+	long long total = HW * (C / 8);
+	dim3 g2((unsigned)std::min<long long>((total + threads - 1) / threads, 148 * 8), (unsigned)N);
+	if (src.dt == DT_F16 && dst.dt == DT_F16)
+		gn_apply_kernel<__half, __half><<<g2, threads, smem, s>>>((const __half*)src.ptr, (__half*)dst.ptr, HW, C, cpg, groups,
+			src.st[3], src.st[0], dst.st[3], dst.st[0], gamma, beta, stats, eps, silu ? 1 : 0);
+	else if (src.dt == DT_F32 && dst.dt == DT_F16)
+		gn_apply_kernel<float, __half><<<g2, threads, smem, s>>>((const float*)src.ptr, (__half*)dst.ptr, HW, C, cpg, groups,
+			src.st[3], src.st[0], dst.st[3], dst.st[0], gamma, beta, stats, eps, silu ? 1 : 0);
+	else if (src.dt == DT_F16 && dst.dt == DT_F32)
+		gn_apply_kernel<__half, float><<<g2, threads, smem, s>>>((const __half*)src.ptr, (float*)dst.ptr, HW, C, cpg, groups,
+			src.st[3], src.st[0], dst.st[3], dst.st[0], gamma, beta, stats, eps, silu ? 1 : 0);
+	else
+		gn_apply_kernel<float, float><<<g2, threads, smem, s>>>((const float*)src.ptr, (float*)dst.ptr, HW, C, cpg, groups,
+			src.st[3], src.st[0], dst.st[3], dst.st[0], gamma, beta, stats, eps, silu ? 1 : 0);
+	g_stats.kernel_launches += 2;
+}
+
+// ------------------------------------------------------------------ LayerNorm (+affine), one warp per row
+// (mlblock_nn.c:58-75; eps 1e-5). Row cached in registers: two exact passes, f32.
+template <typename TI, typename TO, int MAXV>
+__global__ void layernorm_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long rows, int C,
+	long long ld_in, long long ld_out, const float* __restrict__ gamma, const float* __restrict__ beta, float eps)
+{
+	long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+	if (row >= rows) return;
+	int lane = threadIdx.x & 31;
+	const TI* xr = x + row * ld_in;
+	float v[MAXV];
+	float sum = 0.f;
+	#pragma unroll
+	for (int i = 0; i < MAXV; ++i) {
+		int c = lane + i * 32;
+		v[i] = c < C ? (float)xr[c] : 0.f;
+		sum += v[i];
+	}
+	for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(~0u, sum, o);
+	float mean = sum / C, sq = 0.f;
+	#pragma unroll
+	for (int i = 0; i < MAXV; ++i) {
+		int c = lane + i * 32;
+		float d = c < C ? v[i] - mean : 0.f;
+		v[i] = d; sq += d * d;
+	}
+	for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(~0u, sq, o);
+	float rstd = rsqrtf(sq / C + eps);
+	TO* yr = y + row * ld_out;
+	#pragma unroll
+	for (int i = 0; i < MAXV; ++i) {
+		int c = lane + i * 32;
+		if (c < C) {
+			float t = v[i] * rstd;
+			if (gamma) t = t * gamma[c] + (beta ? beta[c] : 0.f);
+			yr[c] = (TO)t;
+		}
+	}
+}
+
+template <typename TI, typename TO>
+static void layernorm_launch(cudaStream_t s, const void* x, void* y, long long rows, int C, long long ldi, long long ldo,
+	const float* g, const float* b, float eps)
+{
+	int wpb = 8;
+	unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+	if (C <= 32 * 24) layernorm_kernel<TI, TO, 24><<<grid, wpb * 32, 0, s>>>((const TI*)x, (TO*)y, rows, C, ldi, ldo, g, b, eps);
+	else if (C <= 32 * 40) layernorm_kernel<TI, TO, 40><<<grid, wpb * 32, 0, s>>>((const TI*)x, (TO*)y, rows, C, ldi, ldo, g, b, eps);
+	else if (C <= 32 * 64) layernorm_kernel<TI, TO, 64><<<grid, wpb * 32, 0, s>>>((const TI*)x, (TO*)y, rows, C, ldi, ldo, g, b, eps);
+	else B200_FATAL("k_layernorm: row length %d too large", C);
+}
+
+void k_layernorm(cudaStream_t s, const View& dst, const View& src, const float* gamma, const float* beta, float eps)
+{
+	int C = (int)src.ne[0];
+	// rows must have a uniform pitch
+	long long rows = src.ne[1] * src.ne[2] * src.ne[3];
+	auto uniform = [](const View& v) {
+		long long p = v.st[1];
+		if (v.ne[1] == 1) p = v.ne[2] > 1 ? v.st[2] : v.st[3];
+		bool ok = v.st[0] == 1;
+		if (v.ne[2] > 1 && v.ne[1] > 1) ok = ok && v.st[2] == v.st[1] * v.ne[1];
+		if (v.ne[3] > 1) ok = ok && v.st[3] == (v.ne[2] > 1 ? v.st[2] * v.ne[2] : v.st[1] * v.ne[1]);
+		return ok ? p : -1;
+	};
+	long long ldi = rows > 1 ? uniform(src) : C, ldo = rows > 1 ? uniform(dst) : C;
+	if (ldi < 0 || ldo < 0) B200_FATAL("k_layernorm: rows are not uniformly strided");
+	if (src.dt == DT_F16 && dst.dt == DT_F16) layernorm_launch<__half, __half>(s, src.ptr, dst.ptr, rows, C, ldi, ldo, gamma, beta, eps);
+	else if (src.dt == DT_F32 && dst.dt == DT_F16) layernorm_launch<float, __half>(s, src.ptr, dst.ptr, rows, C, ldi, ldo, gamma, beta, eps);
+	else if (src.dt == DT_F16 && dst.dt == DT_F32) layernorm_launch<__half, float>(s, src.ptr, dst.ptr, rows, C, ldi, ldo, gamma, beta, eps);
+	else layernorm_launch<float, float>(s, src.ptr, dst.ptr, rows, C, ldi, ldo, gamma, beta, eps);
+	g_stats.kernel_launches++;
+}
+
+// ------------------------------------------------------------------ GEGLU gate (mlblock_nn.c:159-172)
+// h: rows of 2d f16 (value | gate), dst rows of d f16. 8 elements per thread.
+__global__ void geglu_kernel(const __half* __restrict__ h, __half* __restrict__ y, long long rows, int d,
+	long long ldh, long long ldy)
+{
+	int chunks = d / 8;
+	long long total = rows * chunks;
+	for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+		long long r = e / chunks; int ch = (int)(e - r * chunks);
+		uint4 xv = *reinterpret_cast<const uint4*>(h + r * ldh + ch * 8);
+		uint4 gv = *reinterpret_cast<const uint4*>(h + r * ldh + d + ch * 8);
+		const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+		const __half2* gh = reinterpret_cast<const __half2*>(&gv);
+		uint4 ov; __half2* oh = reinterpret_cast<__half2*>(&ov);
+		#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			float2 x = __half22float2(xh[j]), g = __half22float2(gh[j]);
+			oh[j] = __floats2half2_rn(x.x * act_apply(U_GELU, g.x, 0.f), x.y * act_apply(U_GELU, g.y, 0.f));
+		}
+		*reinterpret_cast<uint4*>(y + r * ldy + ch * 8) = ov;
+	}
+}
+void k_geglu(cudaStream_t s, const View& dst, const View& h)
+{
+	int d = (int)dst.ne[0];
+	long long rows = dst.ne[1] * dst.ne[2] * dst.ne[3];
+	if (h.dt != DT_F16 || dst.dt != DT_F16 || d % 8 || h.st[0] != 1 || dst.st[0] != 1)
+		B200_FATAL("k_geglu: unsupported layout");
+	long long total = rows * (d / 8);
+	geglu_kernel<<<grid_for(total, 256), 256, 0, s>>>((const __half*)h.ptr, (__half*)dst.ptr, rows, d, h.st[1], dst.st[1]);
+	g_stats.kernel_launches++;
+}
+
+// ------------------------------------------------------------------ im2col for strided / narrow convs
+__global__ void im2col_kernel(__half* __restrict__ col, long long kpad, V4 x, int KW, int KH,
+	int s0, int s1, int p0, int p1, int d0, int d1, long long OW, long long OH)
+{
+	long long C = x.ne[2], K = (long long)KW * KH * C;
+	long long M = OW * OH * x.ne[3];
+	long long total = M * kpad;
+	for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+		long long m = e / kpad, k = e - m * kpad;
+		float v = 0.f;
+		if (k < K) {
+			long long c = k % C, tap = k / C; int kw = (int)(tap % KW), kh = (int)(tap / KW);
+			long long ow = m % OW, oh = (m / OW) % OH, n = m / (OW * OH);
+			long long iw = ow * s0 + kw * d0 - p0, ih = oh * s1 + kh * d1 - p1;
+			if (iw >= 0 && iw < x.ne[0] && ih >= 0 && ih < x.ne[1])
+				v = ldv(x, iw * x.st[0] + ih * x.st[1] + c * x.st[2] + n * x.st[3]);
+		}
+		col[e] = __float2half_rn(v);
+	}
+}
+void k_im2col(cudaStream_t s, __half* col, int64_t kpad, const View& x, int KW, int KH,
+	int s0, int s1, int p0, int p1, int d0, int d1, int64_t OW, int64_t OH)
+{
+	long long total = OW * OH * x.ne[3] * kpad;
+	im2col_kernel<<<grid_for(total, 256, 4), 256, 0, s>>>(col, kpad, v4(x), KW, KH, s0, s1, p0, p1, d0, d1, OW, OH);
+	g_stats.kernel_launches++;
+}
+
+// conv weight ggml [KW,KH,Cin,Cout] -> rows [Cout][(kh*KW+kw)*Cin + c] with pitch kpad (zero padded)
+__global__ void conv_weight_prep_kernel(__half* __restrict__ dst, long long kpad, V4 w)
+{
+	long long KW = w.ne[0], KH = w.ne[1], C = w.ne[2], OC = w.ne[3], K = KW * KH * C;
+	long long total = OC * kpad;
+	for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+		long long oc = e / kpad, k = e - oc * kpad;
+		float v = 0.f;
+		if (k < K) {
+			long long c = k % C, tap = k / C, kw = tap % KW, kh = tap / KW;
+			v = ldv(w, kw * w.st[0] + kh * w.st[1] + c * w.st[2] + oc * w.st[3]);
+		}
+		dst[e] = __float2half_rn(v);
+	}
+}
+void k_conv_weight_prep(cudaStream_t s, __half* dst, int64_t kpad, const View& w)
+{
+	long long total = w.ne[3] * kpad;
+	conv_weight_prep_kernel<<<grid_for(total, 256, 2), 256, 0, s>>>(dst, kpad, v4(w));
+	g_stats.kernel_launches++;
+}
+
+}  // namespace b200

@@ -1,0 +1,249 @@
+"""Parity of the CUDA engine against the CPU oracle, op by op and block by block, through the
+C ABI (same graph built on both libraries from the same seeded inputs).
+
+Tolerances: the engine keeps activations in f16 between kernels (the reference keeps f32 and
+rounds to f16 at every contraction input), so element-wise agreement is f16-level. The bound used
+per block is max|a-b|/max|b| <= 1e-2 (BASELINE.json north_star per-step UNet tolerance); single
+ops are held to 4e-3.
+"""
+import numpy as np
+import pytest
+from blocks import B, run_both, max_rel_err
+from mlimgsynth_b200.ggml import Graph
+
+pytestmark = pytest.mark.gpu
+OP_TOL = 4e-3
+BLOCK_TOL = 1e-2
+
+
+def check(build, ref, eng, tol, seed=0):
+    (r,), (e,) = run_both(build, ref, eng, seed)
+    assert r.shape == e.shape
+    assert np.isfinite(e).all()
+    err = max_rel_err(e, r)
+    assert err <= tol, "max rel err %.3e > %.1e" % (err, tol)
+    return err
+
+
+# ---------------------------------------------------------------- tensor-core GEMM (linear)
+@pytest.mark.parametrize("M,N,K", [
+    (128, 64, 64), (77, 320, 768), (4096, 320, 320), (1024, 1280, 640), (256, 2560, 320),
+    (64, 1280, 1280), (1, 1280, 320), (300, 200, 72), (130, 24, 8), (2, 4, 2816), (4096, 5120, 640),
+])
+def test_linear(ref, eng, M, N, K):
+    check(lambda b: b.linear(b.inp(M, K), N), ref, eng, OP_TOL)
+
+
+def test_linear_f32_weight(ref, eng):
+    check(lambda b: b.linear(b.inp(5, 96), 48, wdtype=np.float32), ref, eng, OP_TOL)
+
+
+def test_linear_act_residual(ref, eng):
+    def build(b):
+        x = b.inp(300, 320)
+        y = b.linear(x, 320)
+        y = b.g.ggml_gelu_quick_inplace(b.cc, y)
+        z = b.linear(y, 320)
+        return b.g.ggml_add(b.cc, z, x)
+    check(build, ref, eng, OP_TOL)
+
+
+# ---------------------------------------------------------------- convolutions
+@pytest.mark.parametrize("W,H,Cin,Cout,N", [
+    (64, 64, 320, 320, 1), (32, 32, 640, 640, 1), (16, 16, 1280, 640, 1), (8, 8, 1280, 1280, 2),
+    (24, 40, 64, 96, 1), (12, 12, 128, 64, 3), (64, 64, 320, 4, 1), (16, 16, 128, 3, 1), (7, 5, 64, 32, 2),
+])
+def test_conv3x3(ref, eng, W, H, Cin, Cout, N):
+    check(lambda b: b.conv2d(b.inp(N, Cin, H, W), Cout), ref, eng, OP_TOL)
+
+
+@pytest.mark.parametrize("W,H,Cin,Cout,k,s,p", [
+    (64, 64, 4, 320, 3, 1, 1), (32, 32, 320, 320, 3, 2, 1), (17, 17, 64, 64, 3, 2, 0), (32, 32, 320, 640, 1, 1, 0),
+    (16, 16, 4, 4, 1, 1, 0), (16, 16, 3, 128, 3, 1, 1), (16, 16, 8, 8, 1, 1, 0),
+])
+def test_conv_other(ref, eng, W, H, Cin, Cout, k, s, p):
+    check(lambda b: b.conv2d(b.inp(1, Cin, H, W), Cout, k, s, p), ref, eng, OP_TOL)
+
+
+def test_downsample_vae(ref, eng):
+    check(lambda b: b.downsample(b.inp(1, 128, 16, 16), 128, vae=True), ref, eng, OP_TOL)
+
+
+def test_upsample(ref, eng):
+    check(lambda b: b.upsample(b.inp(1, 64, 8, 8), 64), ref, eng, OP_TOL)
+
+
+# ---------------------------------------------------------------- norms and element-wise
+@pytest.mark.parametrize("W,H,C,N", [(64, 64, 320, 1), (8, 8, 1280, 2), (16, 16, 960, 1), (32, 32, 128, 1), (5, 3, 64, 1)])
+def test_groupnorm_silu(ref, eng, W, H, C, N):
+    def build(b):
+        x = b.groupnorm32(b.inp(N, C, H, W, scale=2.0))
+        return b.g.ggml_silu_inplace(b.cc, x)
+    check(build, ref, eng, OP_TOL)
+
+
+@pytest.mark.parametrize("rows,C", [(4096, 320), (77, 768), (64, 1280), (3, 2048), (10, 100)])
+def test_layernorm(ref, eng, rows, C):
+    check(lambda b: b.layer_norm(b.inp(rows, C, scale=3.0)), ref, eng, OP_TOL)
+
+
+def test_geglu_ff(ref, eng):
+    check(lambda b: b.feed_forward(b.inp(256, 320), 320), ref, eng, BLOCK_TOL)
+
+
+@pytest.mark.parametrize("op", ["silu", "gelu", "gelu_quick", "relu", "tanh"])
+def test_unary(ref, eng, op):
+    def build(b):
+        x = b.g.ggml_scale(b.cc, b.inp(7, 33, scale=3.0), 1.5)
+        f = {"silu": b.g.ggml_silu_inplace, "gelu": b.g.ggml_gelu_inplace, "gelu_quick": b.g.ggml_gelu_quick_inplace,
+             "relu": b.g.ggml_relu_inplace, "tanh": b.g.ggml_tanh_inplace}[op]
+        return f(b.cc, x)
+    check(build, ref, eng, OP_TOL)
+
+
+def test_concat_pad_upscale(ref, eng):
+    def build(b):
+        x = b.inp(2, 8, 6, 5); y = b.inp(2, 16, 6, 5)
+        z = b.g.ggml_concat(b.cc, x, y, 2)
+        z = b.g.ggml_pad(b.cc, z, 1, 1, 0, 0)
+        z = b.g.ggml_upscale(b.cc, z, 2, 0)
+        return b.g.ggml_scale(b.cc, z, 0.5)
+    check(build, ref, eng, OP_TOL)
+
+
+def test_timestep_embedding(ref, eng):
+    def build(b):
+        t = b.G.leaf(np.array([981.3], dtype=np.float32))
+        return b.g.ggml_timestep_embedding(b.cc, t, 320, 10000)
+    check(build, ref, eng, OP_TOL)
+
+
+def test_get_rows_pos_add(ref, eng):
+    def build(b):
+        ids = b.G.leaf(b.rng.integers(0, 1000, size=(1, 77)).astype(np.int32))
+        tab = b.G.leaf((b.rng.standard_normal((1000, 64)) * 0.02).astype(np.float16))
+        pos = b.G.leaf((b.rng.standard_normal((77, 64)) * 0.01).astype(np.float32))
+        x = b.g.ggml_reshape_3d(b.cc, ids, 77, 1, 1)
+        x = b.g.ggml_get_rows(b.cc, tab, x)
+        ne = b.ne(x)
+        x = b.g.ggml_reshape_3d(b.cc, x, ne[0], ne[1], ne[3])
+        return b.g.ggml_add(b.cc, x, pos)
+    check(build, ref, eng, OP_TOL)
+
+
+def test_softmax_standalone(ref, eng):
+    def build(b):
+        x = b.g.ggml_scale(b.cc, b.inp(3, 9, 50, scale=2.0), 1.0)
+        x = b.g.ggml_diag_mask_inf_inplace(b.cc, x, 0) if False else x
+        return b.g.ggml_soft_max_inplace(b.cc, x)
+    check(build, ref, eng, OP_TOL)
+
+
+# ---------------------------------------------------------------- attention
+@pytest.mark.parametrize("nq,nk,d_embed,n_head,mask", [
+    (256, 256, 320, 8, False), (64, 77, 640, 8, False), (77, 77, 768, 12, True), (1024, 1024, 640, 10, False),
+    (100, 37, 1280, 8, False),
+])
+def test_attn_mhead(ref, eng, nq, nk, d_embed, n_head, mask):
+    def build(b):
+        x = b.inp(nq, d_embed)
+        c = x if nk == nq else b.inp(nk, 96)
+        return b.attn_mhead(x, c, c, d_embed, d_embed, n_head, mask=mask, bias=mask)
+    check(build, ref, eng, BLOCK_TOL)
+
+
+def test_attn_2d_self_vae(ref, eng):
+    check(lambda b: b.attn_2d_self(b.inp(1, 512, 16, 16)), ref, eng, BLOCK_TOL)
+
+
+# ---------------------------------------------------------------- blocks
+@pytest.mark.parametrize("W,cin,cout,emb", [(32, 320, 320, True), (16, 640, 1280, True), (16, 960, 640, True), (32, 128, 256, False)])
+def test_resnet(ref, eng, W, cin, cout, emb):
+    def build(b):
+        x = b.inp(1, cin, W, W)
+        e = b.inp(1, 1280) if emb else None
+        return b.resnet(x, e, cout)
+    check(build, ref, eng, BLOCK_TOL)
+
+
+def test_resnet_batch2(ref, eng):
+    check(lambda b: b.resnet(b.inp(2, 320, 16, 16), b.inp(2, 1280), 640), ref, eng, BLOCK_TOL)
+
+
+@pytest.mark.parametrize("W,ch,heads", [(32, 320, 8), (16, 640, 8), (8, 1280, 8)])
+def test_spatial_transformer(ref, eng, W, ch, heads):
+    def build(b):
+        x = b.inp(1, ch, W, W)
+        ctx = b.inp(77, 768)
+        return b.spatial_transf(x, ctx, ch, heads)
+    check(build, ref, eng, BLOCK_TOL)
+
+
+def test_clip_layers(ref, eng):
+    def build(b):
+        x = b.inp(77, 768, scale=0.5)
+        for _ in range(3):
+            x = b.clip_layer(x, 768, 12, 3072)
+        return b.layer_norm(x)
+    check(build, ref, eng, BLOCK_TOL)
+
+
+def test_unet_like_down_up(ref, eng):
+    """conv_in -> resnet+transformer -> downsample -> resnet -> upsample -> concat skip -> resnet -> out."""
+    def build(b):
+        g, cc = b.g, b.cc
+        x = b.inp(1, 4, 32, 32)
+        emb = b.inp(1, 1280)
+        ctx = b.inp(77, 768)
+        h0 = b.conv2d(x, 320)
+        h1 = b.resnet(h0, emb, 320)
+        h1 = b.spatial_transf(h1, ctx, 320, 8)
+        h2 = b.downsample(h1, 320)
+        h3 = b.resnet(h2, emb, 640)
+        u = b.upsample(h3, 640)
+        u = g.ggml_concat(cc, u, h1, 2)
+        u = b.resnet(u, emb, 320)
+        u = b.groupnorm32(u)
+        u = g.ggml_silu_inplace(cc, u)
+        return b.conv2d(u, 4)
+    check(build, ref, eng, BLOCK_TOL)
+
+
+# ---------------------------------------------------------------- boundary behaviour
+def test_multi_compute_and_reupload(ref, eng):
+    """MLB_F_MULTI_COMPUTE semantics (mlblock.c:128-134): same graph recomputed with new inputs;
+    weights re-uploaded between computes must take effect (prepared-weight cache invalidation)."""
+    outs = {}
+    for name, lib in (("ref", ref), ("eng", eng)):
+        G = Graph(lib); b = B(G, 3)
+        x = b.inp(1, 64, 16, 16)
+        y = b.conv2d(x, 64)
+        w_leaf = G.leaves[1][0]
+        G.build(y)
+        res = []
+        G.compute(); res.append(G.get(y))
+        G.set(x, G.leaves[0][1] * 2.0)
+        G.compute(); res.append(G.get(y))
+        G.set(w_leaf, (G.leaves[1][1] * 0.5).astype(np.float16))
+        G.compute(); res.append(G.get(y))
+        G.free()
+        outs[name] = res
+    for r, e in zip(outs["ref"], outs["eng"]):
+        assert max_rel_err(e, r) <= OP_TOL
+    assert max_rel_err(outs["eng"][1], outs["eng"][0]) > 0.1
+
+
+def test_lora_merge_graph(ref, eng):
+    """lora.c:55-63: W(f16) += scale * (up . down), result read back through the in-place alias."""
+    def build(b):
+        g, cc = b.g, b.cc
+        n0, n1, r = 320, 640, 16
+        ld = b.G.leaf((b.rng.standard_normal((r, n0)) * 0.1).astype(np.float16))     # [n0, r] ggml
+        lu = b.G.leaf((b.rng.standard_normal((n1, r)) * 0.1).astype(np.float16))     # [r, n1]
+        dst = b.G.leaf((b.rng.standard_normal((n1, n0)) * 0.05).astype(np.float16))  # [n0, n1]
+        t = g.ggml_cont(cc, g.ggml_transpose(cc, ld))
+        t = g.ggml_mul_mat(cc, lu, t)
+        t = g.ggml_cont(cc, g.ggml_transpose(cc, t))
+        t = g.ggml_scale_inplace(cc, t, 0.8)
+        return g.ggml_add_inplace(cc, dst, t)
+    check(build, ref, eng, OP_TOL)
