@@ -51,7 +51,25 @@ def build(verbose=False, force=False):
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
+    build_host(so, verbose, force)
     return so
+
+
+def build_host(engine_so, verbose=False, force=False):
+    """The C host layer (mlis_* API, model builders, sampler): libmlimgsynth_b200.so, plain gcc."""
+    hdir = os.path.join(CSRC, "host")
+    srcs = sorted(glob.glob(os.path.join(hdir, "*.c")))
+    deps = srcs + glob.glob(os.path.join(hdir, "*.h")) + glob.glob(os.path.join(ROOT, "include", "*.h")) + [engine_so]
+    out = os.path.join(LIB, "libmlimgsynth_b200.so")
+    if not (force or _stale(out, deps)):
+        return out
+    cmd = ["gcc", "-std=gnu11", "-O2", "-g", "-fPIC", "-shared", "-Wall", "-Wno-unused-function", "-fvisibility=default",
+           "-I", os.path.join(ROOT, "include"), "-I", hdir, "-o", out] + srcs + \
+          ["-L", LIB, "-lggml_b200", "-Wl,-rpath,$ORIGIN", "-Wl,--no-undefined", "-lm", "-ldl"]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return out
 
 
 if __name__ == "__main__":

@@ -46,6 +46,12 @@ namespace b200 { bool g_dryrun() { return dryrun(); } }
 static cudaStream_t g_stream = nullptr;   // tensor_set/get have no backend argument: one engine stream per process
 static int g_device = -1;
 
+cudaStream_t b200_engine_stream()
+{
+	if (!g_stream) B200_FATAL("no B200 backend initialised (call ggml_backend_init_* first)");
+	return g_stream;
+}
+
 extern "C" {
 
 ggml_backend_t ggml_backend_init_by_name(const char* name, const char* params)

@@ -48,6 +48,8 @@ struct Backend;
 Plan* plan_build(Backend* be, ggml_cgraph* g);
 void  plan_run(Plan* p);
 void  plan_free(Plan* p);
+void  profile_enable(bool on);
+bool  profile_get(int kind, double* ms, double* flops, double* bytes, uint64_t* launches);
 
 // Counters exposed through ggml_backend_reg_get_proc_address("ggml_b200_stats").
 struct Stats {

@@ -76,6 +76,18 @@ struct Plan {
 };
 
 bool g_dryrun();
+// ---- per-kernel-family profile (ggml_b200_profile_*): eager run with CUDA events around each step
+struct ProfAcc { double ms = 0, flops = 0, bytes = 0; uint64_t launches = 0; };
+static bool g_profile = false;
+static ProfAcc g_prof[32];
+void profile_enable(bool on) { g_profile = on; if (on) for (auto& a : g_prof) a = ProfAcc(); }
+bool profile_get(int kind, double* ms, double* flops, double* bytes, uint64_t* launches)
+{
+	if (kind < 0 || kind >= 32) return false;
+	*ms = g_prof[kind].ms; *flops = g_prof[kind].flops; *bytes = g_prof[kind].bytes; *launches = g_prof[kind].launches;
+	return true;
+}
+
 static bool env_flag(const char* n) { const char* e = getenv(n); return e && *e && *e != '0'; }
 
 // ------------------------------------------------------------------ PT helpers
@@ -966,6 +978,37 @@ Plan* plan_build(Backend* be, ggml_cgraph* g)
 	return P;
 }
 
+static void step_cost(const Step& s, double* flops, double* bytes)
+{
+	auto nb = [](const PT& p) { return (double)p.numel() * dt_size(p.dt); };
+	*flops = 0; *bytes = nb(s.out);
+	for (int i = 0; i < s.n_in; ++i) *bytes += nb(s.in[i]);
+	if (s.has_residual) *bytes += nb(s.residual);
+	if (s.kind == S_GEMM_TC || s.kind == S_CONV_TC) *flops = 2.0 * s.M * s.N * s.K;
+	else if (s.kind == S_GEMM_SIMT) *flops = 2.0 * s.in[0].ne[0] * (double)s.out.numel();
+	else if (s.kind == S_ATTENTION) *flops = 4.0 * s.in[0].ne[0] * s.in[0].ne[1] * s.in[1].ne[1] * s.in[0].ne[2] * s.in[0].ne[3];
+}
+
+static void plan_run_profiled(Plan* P)
+{
+	cudaStream_t st = P->be->stream;
+	cudaEvent_t e0, e1;
+	CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+	if (P->zero_bytes) CUDA_CHECK(cudaMemsetAsync((char*)P->arena + P->bufs[P->zero_buf].off, 0, P->zero_bytes, st));
+	for (Step& s : P->steps) {
+		uint64_t l0 = g_stats.kernel_launches;
+		CUDA_CHECK(cudaEventRecord(e0, st));
+		run_step(P, s, st);
+		CUDA_CHECK(cudaEventRecord(e1, st));
+		CUDA_CHECK(cudaEventSynchronize(e1));
+		float ms = 0; CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+		double fl, by; step_cost(s, &fl, &by);
+		ProfAcc& a = g_prof[s.kind];
+		a.ms += ms; a.flops += fl; a.bytes += by; a.launches += g_stats.kernel_launches - l0;
+	}
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+}
+
 void plan_run(Plan* P)
 {
 	cudaStream_t st = P->be->stream;
@@ -974,6 +1017,7 @@ void plan_run(Plan* P)
 		uint64_t v = trec(s.leaf)->version;
 		if (v != s.leaf_version) { run_step(P, s, st); s.leaf_version = v; }
 	}
+	if (g_profile) { plan_run_profiled(P); return; }
 	if (P->use_graph && !P->exec) {
 		// first run: execute eagerly once (creates tensor maps, sets function attributes), then capture
 		uint64_t l0 = g_stats.kernel_launches;
