@@ -66,15 +66,16 @@ ggml_backend_t ggml_backend_init_by_name(const char* name, const char* params)
 	enumerate_devices();
 	int dev = 0;
 	if (name && *name) {
-		// accepted: "B200", "CUDA", "GPU", "CUDA<i>", "B200:<i>"
-		const char* p = name;
-		while (*p && (*p < '0' || *p > '9')) p++;
-		if (*p) dev = atoi(p);
+		// accepted: "B200", "CUDA", "GPU" (device LOCAL_RANK or 0), "B200:<i>", "CUDA:<i>", "CUDA<i>"
 		if (name[0] == 'C' && name[1] == 'P') {
 			B200_LOG("backend '%s' requested, but this library has no CPU backend (B200 engine only)", name);
 			return nullptr;
 		}
-		if (const char* e = getenv("LOCAL_RANK")) { if (!*p) dev = atoi(e); }
+		const char* colon = strchr(name, ':');
+		bool explicit_dev = false;
+		if (colon && colon[1] >= '0' && colon[1] <= '9') { dev = atoi(colon + 1); explicit_dev = true; }
+		else if (!strncmp(name, "CUDA", 4) && name[4] >= '0' && name[4] <= '9') { dev = atoi(name + 4); explicit_dev = true; }
+		if (!explicit_dev) if (const char* e = getenv("LOCAL_RANK")) dev = atoi(e);
 	} else if (const char* e = getenv("LOCAL_RANK")) dev = atoi(e);
 	if (g_devs.empty()) { B200_LOG("no CUDA device visible: the B200 engine cannot start (there is no CPU fallback)"); return nullptr; }
 	if (dev < 0 || dev >= (int)g_devs.size()) { B200_LOG("device index %d out of range (%zu devices)", dev, g_devs.size()); return nullptr; }

@@ -126,6 +126,7 @@ MLIS_Ctx* mlis_ctx_create_i(int version)
 	(void)version;
 	MLIS_Ctx* S = xcalloc(1, sizeof(*S));
 	S->signature = CTX_SIGNATURE;
+	unet_params_init();            /* sigma tables are needed before the first UNet graph exists (dnsamp_init) */
 	S->cfg_scale = 7;              /* mlimgsynth.c:474 */
 	S->n_batch = 1;
 	S->wtype = GGML_TYPE_F16;
@@ -188,7 +189,8 @@ static int model_type_set(MLIS_Ctx* S, int mt)
 	case MLIS_MODEL_TYPE_SD1: S->unet_p = &g_unet_sd1; S->clip_p = &g_clip_vit_l_14; if (!S->clip_skip) S->clip_skip = 1; break;
 	case MLIS_MODEL_TYPE_SD2: S->unet_p = &g_unet_sd2; S->clip_p = &g_clip_vit_h_14; if (!S->clip_skip) S->clip_skip = 2; break;
 	case MLIS_MODEL_TYPE_SDXL: S->unet_p = &g_unet_sdxl; S->vae_p = &g_vae_sdxl; S->clip_p = &g_clip_vit_l_14; S->clip2_p = &g_clip_vit_bigg_14;
-		if (!S->clip_skip) S->clip_skip = 2; break;
+		if (!S->clip_skip) S->clip_skip = 2;
+		break;
 	default: FAIL(MLIS_E_OPT_VALUE, "invalid model type %d", mt);
 	}
 	if (!S->width) { int d = mt == MLIS_MODEL_TYPE_SD1 ? 512 : mt == MLIS_MODEL_TYPE_SD2 ? 768 : 1024; S->width = S->height = d; }
@@ -276,7 +278,9 @@ static int option_apply(MLIS_Ctx* S, MLIS_Option id, const Arg* a, int n_arg)
 	case MLIS_OPT_IMAGE_MASK: image_to_tensors(S, a[0].p, true); break;
 	case MLIS_OPT_NO_DECODE: if (a[0].i) S->flags |= CF_NO_DECODE; else S->flags &= ~CF_NO_DECODE; break;
 	case MLIS_OPT_TENSOR_USE_FLAGS: S->tuflags = (int)a[0].i; break;
-	case MLIS_OPT_SEED: g_rng.seed = (uint64_t)a[0].i; break;   /* the offset keeps counting (options_set.c.h:162-168) */
+	case MLIS_OPT_SEED: g_rng.seed = (uint64_t)a[0].i;   /* the offset keeps counting (options_set.c.h:162-168) ... */
+		if (n_arg > 1) g_rng.offset = (uint32_t)a[1].i;       /* ... unless given explicitly: "seed", "42,0" (addition, string form only) */
+		break;
 	case MLIS_OPT_VAE_TILE: S->vae_tile = (int)a[0].i; break;
 	case MLIS_OPT_UNET_SPLIT: case MLIS_OPT_THREADS: case MLIS_OPT_DUMP_FLAGS: break;   /* accepted, no effect on B200 */
 	case MLIS_OPT_WEIGHT_TYPE:
@@ -303,7 +307,7 @@ static const char* option_sig(MLIS_Option id)
 	case MLIS_OPT_LORA_CLEAR: return "";
 	case MLIS_OPT_IMAGE_DIM: return "ii";
 	case MLIS_OPT_CFG_SCALE: case MLIS_OPT_F_T_INI: case MLIS_OPT_F_T_END: case MLIS_OPT_S_NOISE: case MLIS_OPT_S_ANCESTRAL: return "f";
-	case MLIS_OPT_SEED: return "u";
+	case MLIS_OPT_SEED: return "uI";
 	case MLIS_OPT_IMAGE: case MLIS_OPT_IMAGE_MASK: return "p";
 	case MLIS_OPT_CALLBACK: case MLIS_OPT_ERROR_HANDLER: return "pp";
 	case MLIS_OPT_METHOD: case MLIS_OPT_SCHEDULER: case MLIS_OPT_MODEL_TYPE: case MLIS_OPT_WEIGHT_TYPE: case MLIS_OPT_LOG_LEVEL: return "e";
@@ -322,11 +326,13 @@ int mlis_option_set(MLIS_Ctx* S, MLIS_Option id, ...)
 		switch (sig[n]) {
 		case 's': case 'S': a[n].s = va_arg(ap, const char*); break;
 		case 'i': case 'e': a[n].i = va_arg(ap, int); break;
+		case 'I': goto done;   /* string-form extension only */
 		case 'f': case 'F': a[n].f = va_arg(ap, double); break;
 		case 'u': a[n].i = (long long)va_arg(ap, uint64_t); break;
 		case 'p': if (n == 0) a[n].p = va_arg(ap, const void*); else a[n].p2 = va_arg(ap, void*); break;
 		}
 	}
+done:
 	va_end(ap);
 	API_TRY(option_apply(S, id, a, n), "mlis_option_set");
 	return 1;
@@ -348,13 +354,13 @@ int mlis_option_set_str(MLIS_Ctx* S, const char* name, const char* value)
 		const char* e = whole ? v + strlen(v) : strchr(v, ',');
 		if (!e) e = v + strlen(v);
 		bool present = e > v || (n == 0);
-		bool optional = sig[n] == 'S' || sig[n] == 'F';
+		bool optional = sig[n] == 'S' || sig[n] == 'F' || sig[n] == 'I';
 		if (!present && optional) break;
 		if (whole) a[n].s = v;
 		else { snprintf(buf[n], sizeof(buf[n]), "%.*s", (int)(e - v), v); a[n].s = buf[n]; }
 		char* tail = NULL;
 		switch (sig[n]) {
-		case 'i': a[n].i = strtoll(a[n].s, &tail, 0);
+		case 'i': case 'I': a[n].i = strtoll(a[n].s, &tail, 0);
 			if (tail == a[n].s) { if (!strcmp(a[n].s, "true")) a[n].i = 1; else if (!strcmp(a[n].s, "false")) a[n].i = 0; else goto bad; }
 			break;
 		case 'u': a[n].i = (long long)strtoull(a[n].s, &tail, 0); if (tail == a[n].s) goto bad; break;

@@ -185,8 +185,11 @@ static int run_tiled(CodecState* S, const float* in_dev, int iw, int ih, int cin
 			CHECK(mlctx_compute(C));
 			if (single) { copy_region(out_dev, ow, oh, 0, 0, tout, tw_o, th_o, 0, 0, tw_o, th_o, cout); continue; }
 			int d0 = i0 ? k : 0, d1 = i1 ? k : 0;
+			/* a dim that one tile covers entirely is copied whole (the reference leaves its last k rows/columns
+			 * unwritten in that case, vae.c:381-384 with n == full size) */
+			int c0 = n0 == iw ? n0 : n0 - k, c1 = n1 == ih ? n1 : n1 - k;
 			copy_region(out_dev, ow, oh, (i0 + d0) * up / down, (i1 + d1) * up / down, tout, tw_o, th_o,
-				d0 * up / down, d1 * up / down, (n0 - k) * up / down, (n1 - k) * up / down, cout);
+				d0 * up / down, d1 * up / down, c0 * up / down, c1 * up / down, cout);
 		}
 	}
 	return 1;

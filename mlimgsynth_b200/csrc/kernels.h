@@ -34,6 +34,13 @@ void k_conv_weight_prep(cudaStream_t s, __half* dst, int64_t kpad, const View& w
 // o[d,q,h,b] = softmax_k(scale * q.k)[.] v ; q:[d,nq,H,B] k:[d,nk,H,B] v given as [nk,d,H,B] (ggml V^T view)
 void k_attention(cudaStream_t s, const View& o, const View& q, const View& k, const View& v, float scale, bool causal);
 
+// tcgen05 flash attention (attn_tc.cu): non-causal, d <= 128, f16 token-major operands
+struct AttnTC;
+bool    attn_tc_supported(const View& o, const View& q, const View& k, const View& v, bool causal);
+AttnTC* attn_tc_prepare(const View& o, const View& q, const View& k, const View& v, float scale);
+void    attn_tc_launch(cudaStream_t s, AttnTC* a);
+void    attn_tc_free(AttnTC* a);
+
 // ---- tensor-core GEMM / implicit conv (gemm_tc.cu)
 struct GemmEpilogue {
 	const float* bias = nullptr;       // [N]

@@ -54,6 +54,7 @@ struct Step {
 	int64_t M = 0, N = 0, K = 0, lda = 0, ldb = 0, ldc = 0;
 	int64_t conv_n = 0, conv_h = 0, conv_w = 0, conv_c = 0;
 	GemmTC* tc = nullptr;
+	AttnTC* atc = nullptr; bool atc_checked = false;
 	size_t stats_off = 0;               // groupnorm statistics slot in the zero region
 	const ggml_tensor* leaf = nullptr;  // weight prep: source leaf (+ version it was prepared at)
 	uint64_t leaf_version = ~0ull;
@@ -912,9 +913,17 @@ static void run_step(Plan* P, Step& s, cudaStream_t st)
 			s.iparam[4], s.iparam[5], s.iparam[6], s.iparam[7], s.M, s.N);
 		break;
 	case S_WPREP_CONV: k_conv_weight_prep(st, (__half*)buf_ptr(P, s.out), s.iparam[0], view_of(P, s.in[0])); break;
-	case S_ATTENTION:
-		k_attention(st, view_of(P, s.out), view_of(P, s.in[0]), view_of(P, s.in[1]), view_of(P, s.in[2]), s.fparam, s.iparam[0] != 0);
-		break;
+	case S_ATTENTION: {
+		View o = view_of(P, s.out), q = view_of(P, s.in[0]), k = view_of(P, s.in[1]), v = view_of(P, s.in[2]);
+		if (!s.atc_checked) {
+			s.atc_checked = true;
+			const char* e = getenv("GGML_B200_ATTN");
+			bool simt = e && !strcmp(e, "simt");
+			if (!simt && attn_tc_supported(o, q, k, v, s.iparam[0] != 0)) s.atc = attn_tc_prepare(o, q, k, v, s.fparam);
+		}
+		if (s.atc) attn_tc_launch(st, s.atc);
+		else k_attention(st, o, q, k, v, s.fparam, s.iparam[0] != 0);
+	} break;
 	case S_GEMM_TC: case S_CONV_TC: {
 		if (!s.tc) {
 			GemmEpilogue ep;
@@ -1056,7 +1065,7 @@ void plan_free(Plan* P)
 	if (!P) return;
 	if (g_dryrun()) { delete P; return; }
 	cudaStreamSynchronize(P->be->stream);
-	for (Step& s : P->steps) if (s.tc) gemm_tc_free(s.tc);
+	for (Step& s : P->steps) { if (s.tc) gemm_tc_free(s.tc); if (s.atc) attn_tc_free(s.atc); }
 	if (P->exec) cudaGraphExecDestroy(P->exec);
 	if (P->arena) cudaFree(P->arena);
 	if (P->persist) cudaFree(P->persist);
