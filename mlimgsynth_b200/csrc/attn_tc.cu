@@ -3,33 +3,38 @@
 // softmax, PV with the [nk,nq,heads] f32 score tensor materialised three times) for the UNet's
 // self/cross attention (mlblock_nn.c:190-231) and the VAE's spatial attention (vae.c:46-74).
 //
-// One CTA owns 128 query rows of one (head, image) and streams the keys in blocks of 128:
-//   warp 0      TMA producer: Q once, then a ring of K and V tiles (4-D tensor maps straight over the
-//               token-major [token][head][d] activations: no head split/merge copies exist)
-//   warp 1      MMA issuer: S = Q K^T (tcgen05.mma, K-major operands) into one of two TMEM score
-//               buffers, then PV = P V (A = P from shared memory, B = V as an MN-major operand, so V
-//               is consumed in its natural [key][d] layout) into a TMEM output tile
-//   warps 2..5  softmax + accumulate, one query row per thread: tcgen05.ld of the scores, running
-//               max / sum in the exp2 domain, P written as f16 into the 128B-swizzled K-major tile
-//               the second MMA reads; the PV tile of the previous block is added to the register
-//               accumulator with the usual online-softmax correction while the tensor core works on
-//               the next block.
-// Head dims 40/80 (SD1.x) are handled by TMA zero-fill up to the next multiple of 16.
+// One CTA owns TWO tiles of 128 query rows of one (head, image) and streams the keys in blocks of
+// 128, ping-ponging the tiles so the tensor core works on one while the other is in softmax:
+//   warp 0        TMA producer: both Q tiles once, then a ring of K and V tiles (4-D tensor maps
+//                 straight over the token-major [token][head][d] activations: the reference's head
+//                 split/merge copies, mlblock_nn.c:204-226, do not exist)
+//   warp 1        MMA issuer (one thread): S_t = Q_t K^T into the tile's TMEM score buffer
+//                 (tcgen05.mma, both operands K-major from shared memory); O_t,j = P_t V with the
+//                 A operand P read FROM TENSOR MEMORY (the softmax warps overwrite the consumed part
+//                 of S_t with the f16 probabilities) and V as an MN-major B operand, i.e. in its
+//                 natural [key][d] layout
+//   warps 2..5 / 6..9   softmax + accumulate for tile a / b, one query row per thread: tcgen05.ld of
+//                 the scores, running max / sum in the exp2 domain (ex2.approx), P written back with
+//                 tcgen05.st; the PV tile of the previous block is folded into the register
+//                 accumulator with the online-softmax correction while the tensor core is busy.
+// Head dims 40 / 80 (SD1.x) are handled by TMA zero-fill up to the next multiple of 16.
+// Roofline: tensor (4*nq*nk*d FLOP per head); for d <= 64 the MUFU.EX2 rate (16/clk/SM) is the
+// practical limit (1024 clk per 128x128 tile vs 2*(d/16)*64 clk of MMA).
 #include "kernels.h"
 #include "tc_common.cuh"
 #include <algorithm>
 
 namespace b200 {
 
-constexpr int AQ = 128;      // queries per CTA
+constexpr int AQ = 128;      // queries per tile (two tiles per CTA)
 constexpr int AK = 128;      // keys per block
 constexpr int ACH = 64;      // columns per TMA chunk (128 B)
 constexpr int CHUNK_BYTES = 128 * 128;   // [128 rows][64 f16]
 constexpr int A_TMEM_COLS = 512;
-constexpr int A_MAX_STAGES = 3;
+constexpr int A_MAX_STAGES = 4;
 
 struct AttnParams {
-	int d, d16, dchunks, nq, nk, H, B, stages, pbufs, nblk;
+	int d, d16, dchunks, nq, nk, H, B, stages, nblk;
 	float scale_log2;
 	void* o; long long so_t, so_h, so_b;
 };
@@ -41,41 +46,56 @@ struct AttnTC {
 	size_t smem;
 };
 
+__device__ __forceinline__ float ex2_approx(float x)
+{ float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r)
+{
+	asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+		:: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+		   "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem desc]   (A operand from tensor memory)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+		"tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+		:: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 template <int D16MAX>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
 	const AttnParams p)
 {
 	extern __shared__ __align__(1024) uint8_t smem_raw[];
 	uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 	const int tile_bytes = p.dchunks * CHUNK_BYTES;
-	uint8_t* sQ = smem;
-	uint8_t* sK = sQ + tile_bytes;
-	uint8_t* sV = sK + (size_t)p.stages * tile_bytes;
-	uint8_t* sP = sV + (size_t)p.stages * tile_bytes;
-	uint64_t* bars = (uint64_t*)(sP + (size_t)p.pbufs * 2 * CHUNK_BYTES);
-	uint64_t* q_full = bars;
-	uint64_t* k_full = bars + 1;                    // [stages]
+	uint8_t* sQ = smem;                                   // [2 tiles]
+	uint8_t* sK = sQ + 2 * tile_bytes;                    // [stages]
+	uint8_t* sV = sK + (size_t)p.stages * tile_bytes;     // [stages]
+	uint64_t* bars = (uint64_t*)(sV + (size_t)p.stages * tile_bytes);
+	uint64_t* q_full = bars;                        // [2]
+	uint64_t* k_full = q_full + 2;                  // [stages]
 	uint64_t* k_empty = k_full + A_MAX_STAGES;
 	uint64_t* v_full = k_empty + A_MAX_STAGES;
 	uint64_t* v_empty = v_full + A_MAX_STAGES;
-	uint64_t* s_full = v_empty + A_MAX_STAGES;      // [2]
-	uint64_t* s_empty = s_full + 2;
-	uint64_t* p_full = s_empty + 2;                 // [2]
-	uint64_t* p_empty = p_full + 2;
-	uint64_t* pv_full = p_empty + 2;
-	uint64_t* pv_empty = pv_full + 1;
-	uint32_t* tmem_slot = (uint32_t*)(pv_empty + 1);
+	uint64_t* s_full = v_empty + A_MAX_STAGES;      // [2 tiles]  QK done
+	uint64_t* p_full = s_full + 2;                  // [2 tiles]  probabilities written (128 arrivals)
+	uint64_t* pv_full = p_full + 2;                 // [2 tiles]  PV done
+	uint64_t* pv_empty = pv_full + 2;               // [2 tiles]  PV tile consumed (128 arrivals)
+	uint32_t* tmem_slot = (uint32_t*)(pv_empty + 2);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int q0 = blockIdx.x * AQ, h = blockIdx.y, b = blockIdx.z;
+	const int q0 = blockIdx.x * (2 * AQ), h = blockIdx.y, b = blockIdx.z;
+	const int ntile = (q0 + AQ < p.nq) ? 2 : 1;     // the second tile may be entirely out of range
 
 	if (threadIdx.x == 0) {
 		tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
-		mbar_init(q_full, 1);
 		for (int s = 0; s < p.stages; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-		for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 128); mbar_init(&p_full[i], 128); mbar_init(&p_empty[i], 1); }
-		mbar_init(pv_full, 1); mbar_init(pv_empty, 128);
+		for (int t = 0; t < 2; ++t) { mbar_init(&q_full[t], 1); mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 128); mbar_init(&pv_full[t], 1); mbar_init(&pv_empty[t], 128); }
 		fence_barrier_init();
 	}
 	if (warp == 1) tmem_alloc(tmem_slot, A_TMEM_COLS);
@@ -83,13 +103,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 	__syncthreads();
 	tc_fence_after();
 	const uint32_t tmem_base = *tmem_slot;
-	const uint32_t tm_S[2] = { tmem_base, tmem_base + 128 };
-	const uint32_t tm_PV = tmem_base + 256;
+	// TMEM columns: S_a [0,128) (P_a aliases [0,64)), S_b [128,256), O_a tile [256,384), O_b tile [384,512)
 
 	if (warp == 0) {
 		if (lane == 0) {
-			mbar_expect_tx(q_full, tile_bytes);
-			for (int c = 0; c < p.dchunks; ++c) tma_load_4d(sQ + c * CHUNK_BYTES, &tmQ, q_full, c * ACH, q0, h, b);
+			for (int t = 0; t < ntile; ++t) {
+				mbar_expect_tx(&q_full[t], tile_bytes);
+				for (int c = 0; c < p.dchunks; ++c) tma_load_4d(sQ + t * tile_bytes + c * CHUNK_BYTES, &tmQ, &q_full[t], c * ACH, q0 + t * AQ, h, b);
+			}
 			for (int j = 0; j < p.nblk; ++j) {
 				const int s = j % p.stages; const uint32_t ph = (uint32_t)(j / p.stages) & 1;
 				mbar_wait(&k_empty[s], ph ^ 1);
@@ -103,13 +124,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 	} else if (warp == 1) {
 		if (lane == 0) {
 			const uint32_t idesc_qk = make_idesc_f16(AQ, AK, 0, 0);
-			const uint32_t idesc_pv = make_idesc_f16(AQ, p.d16, 0, 1);     // B = V, MN-major ([key][d], d contiguous)
-			const uint32_t q_addr = smem_u32(sQ);
-			auto issue_qk = [&](int j) {
+			const uint32_t idesc_pv = make_idesc_f16(AQ, p.d16, 0, 1);     // A = P (TMEM), B = V MN-major ([key][d], d contiguous)
+			auto issue_qk = [&](int t, int j) {
 				const int s = j % p.stages;
-				mbar_wait(&k_full[s], (uint32_t)(j / p.stages) & 1);
-				mbar_wait(&s_empty[j & 1], ((uint32_t)(j >> 1) & 1) ^ 1);
-				tc_fence_after();
+				if (t == 0) { mbar_wait(&k_full[s], (uint32_t)(j / p.stages) & 1); tc_fence_after(); }
+				const uint32_t q_addr = smem_u32(sQ + t * tile_bytes);
 				const uint32_t k_addr = smem_u32(sK + (size_t)s * tile_bytes);
 				int first = 1;
 				for (int c = 0; c < p.dchunks; ++c)
@@ -117,140 +136,157 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 						if (c * ACH + kk * 16 >= p.d16) break;
 						uint64_t ad = make_smem_desc_sw128(q_addr + c * CHUNK_BYTES + kk * 32, 16, 1024);
 						uint64_t bd = make_smem_desc_sw128(k_addr + c * CHUNK_BYTES + kk * 32, 16, 1024);
-						umma_f16(tm_S[j & 1], ad, bd, idesc_qk, first ? 0u : 1u);
+						umma_f16(tmem_base + t * 128, ad, bd, idesc_qk, first ? 0u : 1u);
 						first = 0;
 					}
-				umma_commit(&s_full[j & 1]);
-				umma_commit(&k_empty[s]);
+				umma_commit(&s_full[t]);
+				if (t == ntile - 1) umma_commit(&k_empty[s]);
 			};
-			mbar_wait(q_full, 0);
-			issue_qk(0);
-			for (int j = 0; j < p.nblk; ++j) {
-				if (j + 1 < p.nblk) issue_qk(j + 1);
-				const int s = j % p.stages, pb = j % p.pbufs;
-				mbar_wait(&v_full[s], (uint32_t)(j / p.stages) & 1);
-				mbar_wait(&p_full[pb], (uint32_t)(j / p.pbufs) & 1);
-				mbar_wait(pv_empty, ((uint32_t)j & 1) ^ 1);
+			auto issue_pv = [&](int t, int j) {
+				const int s = j % p.stages;
+				if (t == 0) mbar_wait(&v_full[s], (uint32_t)(j / p.stages) & 1);
+				mbar_wait(&p_full[t], (uint32_t)j & 1);
+				mbar_wait(&pv_empty[t], ((uint32_t)j & 1) ^ 1);
 				tc_fence_after();
 				const uint32_t v_addr = smem_u32(sV + (size_t)s * tile_bytes);
-				const uint32_t p_addr = smem_u32(sP + (size_t)pb * 2 * CHUNK_BYTES);
 				const int valid = min(AK, p.nk - j * AK);
 				int first = 1;
-				for (int kc = 0; kc < 2; ++kc)
-					for (int kk = 0; kk < 4; ++kk) {
-						const int key = kc * ACH + kk * 16;
-						if (key >= valid) break;
-						uint64_t ad = make_smem_desc_sw128(p_addr + kc * CHUNK_BYTES + kk * 32, 16, 1024);
-						// V tile: rows = keys (128 B each), 8-row swizzle atoms 1024 B apart (SBO), next 64 d-columns CHUNK_BYTES away (LBO)
-						uint64_t bd = make_smem_desc_sw128(v_addr + key * 128, CHUNK_BYTES, 1024);
-						umma_f16(tm_PV, ad, bd, idesc_pv, first ? 0u : 1u);
-						first = 0;
-					}
-				umma_commit(pv_full);
-				umma_commit(&v_empty[s]);
-				umma_commit(&p_empty[pb]);
+				for (int kk = 0; kk < AK / 16; ++kk) {
+					const int key = kk * 16;
+					if (key >= valid) break;
+					// V tile: rows = keys (128 B each), 8-row swizzle atoms 1024 B apart (SBO), next 64 d-columns CHUNK_BYTES away (LBO)
+					uint64_t bd = make_smem_desc_sw128(v_addr + key * 128, CHUNK_BYTES, 1024);
+					// P in tensor memory: 16 keys = 8 packed 32-bit columns per k-step
+					umma_f16_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + kk * 8, bd, idesc_pv, first ? 0u : 1u);
+					first = 0;
+				}
+				umma_commit(&pv_full[t]);
+				if (t == ntile - 1) umma_commit(&v_empty[s]);
+			};
+			for (int t = 0; t < ntile; ++t) { mbar_wait(&q_full[t], 0); }
+			for (int t = 0; t < ntile; ++t) issue_qk(t, 0);
+			for (int j = 0; j < p.nblk; ++j) {
+				for (int t = 0; t < ntile; ++t) {
+					issue_pv(t, j);                             // in-order after it: S_t/P_t may be overwritten
+					if (j + 1 < p.nblk) issue_qk(t, j + 1);
+				}
 			}
 		}
 	} else {
-		// ===== softmax + accumulate: one query row per thread =====
-		const int quarter = warp & 3;
-		const int r = quarter * 32 + lane;
-		const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-		float m = -INFINITY, l = 0.f, corr_saved = 0.f;
-		float acc[D16MAX];
-		#pragma unroll
-		for (int i = 0; i < D16MAX; ++i) acc[i] = 0.f;
+		// ===== softmax + accumulate: group 0 = warps 2..5 (tile a), group 1 = warps 6..9 (tile b) =====
+		const int t = (warp - 2) >> 2;
+		if (t < ntile) {
+			const int quarter = warp & 3;
+			const int r = quarter * 32 + lane;
+			const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+			const uint32_t ts = tmem_base + t * 128 + lane_off;           // scores / probabilities of this row
+			const uint32_t tpv = tmem_base + 256 + t * 128 + lane_off;    // PV tile of this row
+			const float sl2 = p.scale_log2;
+			float m = -INFINITY, l = 0.f, corr_saved = 0.f;
+			float acc[D16MAX];
+			#pragma unroll
+			for (int i = 0; i < D16MAX; ++i) acc[i] = 0.f;
 
-		auto accumulate = [&](int jj, float corr) {
-			mbar_wait(pv_full, (uint32_t)jj & 1);
-			tc_fence_after();
-			#pragma unroll
-			for (int c0 = 0; c0 < D16MAX; c0 += 16) {
-				if (c0 < p.d16) {
-					uint32_t v[16];
-					tmem_ld16(tm_PV + lane_off + c0, v);
-					tmem_ld_wait();
-					#pragma unroll
-					for (int i = 0; i < 16; ++i) acc[c0 + i] = acc[c0 + i] * corr + __uint_as_float(v[i]);
-				}
-			}
-			tc_fence_before();
-			mbar_arrive(pv_empty);
-		};
-
-		for (int j = 0; j < p.nblk; ++j) {
-			const int valid = min(AK, p.nk - j * AK);
-			mbar_wait(&s_full[j & 1], (uint32_t)(j >> 1) & 1);
-			tc_fence_after();
-			const uint32_t ts = tm_S[j & 1] + lane_off;
-			// pass A: row maximum of the valid keys
-			float mx = -INFINITY;
-			#pragma unroll
-			for (int c = 0; c < 4; ++c) {
-				uint32_t v[32];
-				tmem_ld32(ts + c * 32, v);
-				tmem_ld_wait();
+			auto accumulate = [&](int jj, float corr) {
+				mbar_wait(&pv_full[t], (uint32_t)jj & 1);
+				tc_fence_after();
 				#pragma unroll
-				for (int i = 0; i < 32; ++i) if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-			}
-			const float m_new = fmaxf(m, mx * p.scale_log2);
-			const float corr = (m == -INFINITY) ? 0.f : exp2f(m - m_new);
-			// the P tile must have been consumed by the PV MMA that last used this buffer
-			const int pb = j % p.pbufs;
-			mbar_wait(&p_empty[pb], ((uint32_t)(j / p.pbufs) & 1) ^ 1);
-			uint8_t* prow = sP + (size_t)pb * 2 * CHUNK_BYTES + r * 128;
-			float rowsum = 0.f;
-			#pragma unroll
-			for (int c = 0; c < 4; ++c) {
-				uint32_t v[32];
-				tmem_ld32(ts + c * 32, v);
-				tmem_ld_wait();
-				uint32_t packed[16];
-				#pragma unroll
-				for (int i = 0; i < 32; i += 2) {
-					float p0 = (c * 32 + i < valid) ? exp2f(__uint_as_float(v[i]) * p.scale_log2 - m_new) : 0.f;
-					float p1 = (c * 32 + i + 1 < valid) ? exp2f(__uint_as_float(v[i + 1]) * p.scale_log2 - m_new) : 0.f;
-					__half2 hh = __floats2half2_rn(p0, p1);
-					// sum what the tensor core will actually multiply (the f16-rounded probabilities)
-					float2 back = __half22float2(hh);
-					rowsum += back.x + back.y;
-					packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
-				}
-				// 32 keys = 64 B = four 16-byte chunks of this row; key chunk kc = c / 2, chunk index inside the 128 B row = (c & 1) * 4 + q
-				uint8_t* base = prow + (c >> 1) * CHUNK_BYTES;
-				#pragma unroll
-				for (int q = 0; q < 4; ++q) {
-					const int ci = ((c & 1) * 4 + q) ^ (r & 7);       // 128B swizzle: chunk index XOR (row mod 8)
-					*reinterpret_cast<uint4*>(base + ci * 16) = make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
-				}
-			}
-			tc_fence_before();
-			mbar_arrive(&s_empty[j & 1]);          // score buffer may be overwritten by QK(j+2)
-			fence_proxy_async();                   // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-			mbar_arrive(&p_full[pb]);
-			l = l * corr + rowsum;
-			m = m_new;
-			if (j > 0) accumulate(j - 1, corr_saved);
-			corr_saved = corr;
-		}
-		accumulate(p.nblk - 1, corr_saved);
-
-		const long long t = (long long)q0 + r;
-		if (t < p.nq) {
-			const float inv = l > 0.f ? 1.0f / l : 0.f;
-			__half* op = (__half*)p.o + t * p.so_t + (long long)h * p.so_h + (long long)b * p.so_b;
-			const bool vec = ((((uintptr_t)op) & 15) == 0);
-			#pragma unroll
-			for (int c0 = 0; c0 < D16MAX; c0 += 8) {
-				if (c0 < p.d) {
-					if (vec && c0 + 8 <= p.d) {
-						uint4 o4; __half2* hp = reinterpret_cast<__half2*>(&o4);
+				for (int c0 = 0; c0 < D16MAX; c0 += 16) {
+					if (c0 < p.d16) {
+						uint32_t v[16];
+						tmem_ld16(tpv + c0, v);
+						tmem_ld_wait();
 						#pragma unroll
-						for (int i = 0; i < 4; ++i) hp[i] = __floats2half2_rn(acc[c0 + 2 * i] * inv, acc[c0 + 2 * i + 1] * inv);
-						*reinterpret_cast<uint4*>(op + c0) = o4;
+						for (int i = 0; i < 16; ++i) acc[c0 + i] = fmaf(acc[c0 + i], corr, __uint_as_float(v[i]));
+					}
+				}
+				tc_fence_before();
+				mbar_arrive(&pv_empty[t]);
+			};
+
+			for (int j = 0; j < p.nblk; ++j) {
+				const int valid = p.nk - j * AK;      // >= 128 for all but a partial last block
+				mbar_wait(&s_full[t], (uint32_t)j & 1);
+				tc_fence_after();
+				// pass A: row maximum
+				float mx = -INFINITY;
+				if (valid >= AK) {
+					#pragma unroll
+					for (int c = 0; c < 4; ++c) {
+						uint32_t v[32];
+						tmem_ld32(ts + c * 32, v);
+						tmem_ld_wait();
+						#pragma unroll
+						for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+					}
+				} else {
+					#pragma unroll
+					for (int c = 0; c < 4; ++c) {
+						uint32_t v[32];
+						tmem_ld32(ts + c * 32, v);
+						tmem_ld_wait();
+						#pragma unroll
+						for (int i = 0; i < 32; ++i) if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+					}
+				}
+				const float m_new = fmaxf(m, mx * sl2);
+				const float corr = ex2_approx(m - m_new);      // m = -inf on the first block -> 0
+				// pass B: probabilities, packed to f16 pairs and written over the consumed scores
+				float rowsum = 0.f;
+				#pragma unroll
+				for (int c = 0; c < 4; ++c) {
+					uint32_t v[32];
+					tmem_ld32(ts + c * 32, v);
+					tmem_ld_wait();
+					uint32_t packed[16];
+					if (valid >= AK) {
+						#pragma unroll
+						for (int i = 0; i < 32; i += 2) {
+							float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -m_new));
+							float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sl2, -m_new));
+							rowsum += p0 + p1;
+							__half2 hh = __floats2half2_rn(p0, p1);
+							packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+						}
 					} else {
 						#pragma unroll
-						for (int i = 0; i < 8; ++i) if (c0 + i < p.d) op[c0 + i] = __float2half_rn(acc[c0 + i] * inv);
+						for (int i = 0; i < 32; i += 2) {
+							float p0 = (c * 32 + i < valid) ? ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -m_new)) : 0.f;
+							float p1 = (c * 32 + i + 1 < valid) ? ex2_approx(fmaf(__uint_as_float(v[i + 1]), sl2, -m_new)) : 0.f;
+							rowsum += p0 + p1;
+							__half2 hh = __floats2half2_rn(p0, p1);
+							packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+						}
+					}
+					tmem_st16(ts + c * 16, packed);    // columns [16c, 16c+16) lie inside the already consumed scores
+				}
+				tmem_st_wait();
+				tc_fence_before();
+				mbar_arrive(&p_full[t]);
+				l = fmaf(l, corr, rowsum);
+				m = m_new;
+				if (j > 0) accumulate(j - 1, corr_saved);
+				corr_saved = corr;
+			}
+			accumulate(p.nblk - 1, corr_saved);
+
+			const long long tok = (long long)q0 + t * AQ + r;
+			if (tok < p.nq) {
+				const float inv = l > 0.f ? 1.0f / l : 0.f;
+				__half* op = (__half*)p.o + tok * p.so_t + (long long)h * p.so_h + (long long)b * p.so_b;
+				const bool vec = ((((uintptr_t)op) & 15) == 0);
+				#pragma unroll
+				for (int c0 = 0; c0 < D16MAX; c0 += 8) {
+					if (c0 < p.d) {
+						if (vec && c0 + 8 <= p.d) {
+							uint4 o4; __half2* hp = reinterpret_cast<__half2*>(&o4);
+							#pragma unroll
+							for (int i = 0; i < 4; ++i) hp[i] = __floats2half2_rn(acc[c0 + 2 * i] * inv, acc[c0 + 2 * i + 1] * inv);
+							*reinterpret_cast<uint4*>(op + c0) = o4;
+						} else {
+							#pragma unroll
+							for (int i = 0; i < 8; ++i) if (c0 + i < p.d) op[c0 + i] = __float2half_rn(acc[c0 + i] * inv);
+						}
 					}
 				}
 			}
@@ -311,13 +347,11 @@ AttnTC* attn_tc_prepare(const View& o, const View& q, const View& k, const View&
 	p.scale_log2 = scale * 1.4426950408889634f;
 	p.o = o.ptr; p.so_t = o.st[1]; p.so_h = o.st[2]; p.so_b = o.st[3];
 	const size_t tile = (size_t)p.dchunks * CHUNK_BYTES;
-	p.pbufs = 2;
-	p.stages = p.nblk >= 3 ? 3 : std::max(1, p.nblk);
-	auto total = [&]() { return tile * (1 + 2 * p.stages) + (size_t)p.pbufs * 2 * CHUNK_BYTES + 1024 + 256; };
-	while (total() > 220 * 1024 && p.stages > 2) p.stages--;
-	if (total() > 220 * 1024) p.pbufs = 1;
+	p.stages = std::max(1, std::min(p.nblk, A_MAX_STAGES));
+	auto total = [&]() { return tile * (2 + 2 * p.stages) + 1024 + 512; };
+	while (total() > 220 * 1024 && p.stages > 1) p.stages--;
 	a->smem = total();
-	a->grid = dim3((unsigned)((p.nq + AQ - 1) / AQ), (unsigned)p.H, (unsigned)p.B);
+	a->grid = dim3((unsigned)((p.nq + 2 * AQ - 1) / (2 * AQ)), (unsigned)p.H, (unsigned)p.B);
 	bool ok = encode4(&a->tmQ, q.ptr, p.d, p.nq, p.H, p.B, q.st[1], q.st[2], q.st[3]) &&
 	          encode4(&a->tmK, k.ptr, p.d, p.nk, p.H, p.B, k.st[1], k.st[2], k.st[3]) &&
 	          encode4(&a->tmV, v.ptr, p.d, p.nk, p.H, p.B, v.st[0], v.st[2], v.st[3]);   // v is the [nk, d, H, B] view: token stride = st[0]
@@ -333,8 +367,8 @@ void attn_tc_launch(cudaStream_t s, AttnTC* a)
 		CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		attr_set = true;
 	}
-	if (a->p.d16 <= 64) attn_tc_kernel<64><<<a->grid, 192, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
-	else attn_tc_kernel<128><<<a->grid, 192, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+	if (a->p.d16 <= 64) attn_tc_kernel<64><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+	else attn_tc_kernel<128><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
 	g_stats.kernel_launches++;
 }
 

@@ -68,7 +68,7 @@ __device__ __forceinline__ float act_apply_tc(int op, float x)
 }
 
 // ------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p)
 {
 	extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -285,12 +285,15 @@ static int pick_bn(int64_t m_tiles, int64_t N, int sm_count)
 static void finish_setup(GemmTC* g, const GemmEpilogue& ep, int64_t m_tiles, int sm_count)
 {
 	GemmParams& p = g->p;
-	p.BN = pick_bn(m_tiles, p.N, sm_count);
+	// Two CTAs per SM (2 x 256 TMEM columns): while one CTA drains its accumulator through the epilogue
+	// the other keeps the tensor pipe and the TMA queue busy. Shared memory is sized so that exactly
+	// two fit (>= 77 KB each, so never three: a third could not allocate tensor memory).
+	p.BN = pick_bn(m_tiles, p.N, sm_count * 2);
 	size_t stage = (size_t)BM * BK * 2 + (size_t)p.BN * BK * 2;
-	int stages = (int)std::min<size_t>(MAX_STAGES, (200 * 1024) / stage);
+	int stages = (int)std::min<size_t>(MAX_STAGES, (108 * 1024) / stage);
 	stages = std::max(2, std::min(stages, std::max(2, p.num_kb)));
 	p.stages = stages;
-	g->smem = stages * stage + 1024 /*align*/ + (2 * MAX_STAGES + 1) * 8 + 16;
+	g->smem = std::max<size_t>(stages * stage + 1024 /*align*/ + (2 * MAX_STAGES + 1) * 8 + 16, 77 * 1024);
 	g->grid = dim3((unsigned)((p.N + p.BN - 1) / p.BN), (unsigned)m_tiles);
 	p.bias = ep.bias; p.rowvec = ep.rowvec; p.rowvec_dt = ep.rowvec_dt; p.rowvec_stride = ep.rowvec_stride;
 	p.rows_per_image = ep.rows_per_image > 0 ? ep.rows_per_image : 1;

@@ -266,46 +266,56 @@ void k_gemm_simt(cudaStream_t s, const View& c, const View& a, const View& b, bo
 // per-thread f32 partials over <= 64 elements are combined in double.
 // Pass 1: block = 256 threads covers a tile of pixels x all channels (coalesced), per-group partial
 // sums in shared memory, one double atomicAdd pair per group per block.
+// Pass 1. Grid: (pixel tiles x channel slabs, images). A thread owns ONE 8-channel chunk and walks the
+// pixels of the tile with a fixed stride, so its partial sums stay in registers; they are flushed
+// once per thread (run-length combined per group) to shared memory, then once per block to the
+// double-precision statistics in global memory.
 template <typename T>
 __global__ void gn_stats_kernel(const T* __restrict__ x, long long HW, int C, int cpg, int groups,
-	long long img_stride, long long pix_stride, double* __restrict__ stats, int pix_per_block)
+	long long img_stride, long long pix_stride, double* __restrict__ stats, int pix_per_block, int slab_chunks, int nslabs)
 {
 	extern __shared__ float sm[];  // [groups][2]
-	int n = blockIdx.y;
+	const int n = blockIdx.y;
+	const int tile = blockIdx.x / nslabs, slab = blockIdx.x - tile * nslabs;
 	for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sm[i] = 0.f;
 	__syncthreads();
-	long long p0 = (long long)blockIdx.x * pix_per_block;
-	long long np = min(HW - p0, (long long)pix_per_block);
-	const T* base = x + n * img_stride + p0 * pix_stride;
-	int chunks = C / 8;
-	long long items = np * chunks;
-	for (long long it = threadIdx.x; it < items; it += blockDim.x) {
-		long long p = it / chunks; int ch = (int)(it - p * chunks);
-		const T* ptr = base + p * pix_stride + ch * 8;
-		float v[8];
-		if (sizeof(T) == 2) {
-			uint4 raw = *reinterpret_cast<const uint4*>(ptr);
-			const __half2* h = reinterpret_cast<const __half2*>(&raw);
+	const int chunks = C / 8;
+	const int ch = slab * slab_chunks + (int)(threadIdx.x % slab_chunks);
+	const int plane = threadIdx.x / slab_chunks, planes = blockDim.x / slab_chunks;
+	const long long p0 = (long long)tile * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+	if (plane < planes && ch < chunks) {
+		float su[8], sq[8];
+		#pragma unroll
+		for (int j = 0; j < 8; ++j) { su[j] = 0.f; sq[j] = 0.f; }
+		const T* base = x + n * img_stride + ch * 8;
+		for (long long p = p0 + plane; p < p1; p += planes) {
+			const T* ptr = base + p * pix_stride;
+			float v[8];
+			if (sizeof(T) == 2) {
+				uint4 raw = *reinterpret_cast<const uint4*>(ptr);
+				const __half2* h = reinterpret_cast<const __half2*>(&raw);
+				#pragma unroll
+				for (int j = 0; j < 4; ++j) { float2 f = __half22float2(h[j]); v[2*j] = f.x; v[2*j+1] = f.y; }
+			} else {
+				#pragma unroll
+				for (int j = 0; j < 8; ++j) v[j] = (float)ptr[j];
+			}
 			#pragma unroll
-			for (int j = 0; j < 4; ++j) { float2 f = __half22float2(h[j]); v[2*j] = f.x; v[2*j+1] = f.y; }
-		} else {
-			#pragma unroll
-			for (int j = 0; j < 8; ++j) v[j] = (float)ptr[j];
+			for (int j = 0; j < 8; ++j) { su[j] += v[j]; sq[j] += v[j] * v[j]; }
 		}
-		// run-length combine channels of the same group before touching shared memory
 		int g = (ch * 8) / cpg;
-		float su = 0.f, sq = 0.f;
+		float a = 0.f, b = 0.f;
 		#pragma unroll
 		for (int j = 0; j < 8; ++j) {
 			int gj = (ch * 8 + j) / cpg;
-			if (gj != g) { atomicAdd(&sm[g * 2], su); atomicAdd(&sm[g * 2 + 1], sq); su = 0.f; sq = 0.f; g = gj; }
-			su += v[j]; sq += v[j] * v[j];
+			if (gj != g) { atomicAdd(&sm[g * 2], a); atomicAdd(&sm[g * 2 + 1], b); a = 0.f; b = 0.f; g = gj; }
+			a += su[j]; b += sq[j];
 		}
-		atomicAdd(&sm[g * 2], su); atomicAdd(&sm[g * 2 + 1], sq);
+		atomicAdd(&sm[g * 2], a); atomicAdd(&sm[g * 2 + 1], b);
 	}
 	__syncthreads();
 	for (int i = threadIdx.x; i < groups * 2; i += blockDim.x)
-		atomicAdd(&stats[(long long)n * groups * 2 + i], (double)sm[i]);
+		if (sm[i] != 0.f) atomicAdd(&stats[(long long)n * groups * 2 + i], (double)sm[i]);
 }
 
 template <typename TI, typename TO>
@@ -369,13 +379,17 @@ void k_groupnorm(cudaStream_t s, const View& dst, const View& src, const float* 
 	if (src.st[2] != 1 || dst.st[2] != 1 || C % 8 || src.st[1] != W * src.st[0] || dst.st[1] != W * dst.st[0])
 		B200_FATAL("k_groupnorm: unsupported layout (C=%d)", C);
 	int threads = 256;
-	int pix_per_block = 64;
-	dim3 g1((unsigned)((HW + pix_per_block - 1) / pix_per_block), (unsigned)N);
+	int chunks = C / 8;
+	int slab_chunks = std::min(chunks, 64), nslabs = (chunks + slab_chunks - 1) / slab_chunks;
+	int planes = threads / slab_chunks;
+	int pix_per_block = planes * 16;                  // 16 pixels per thread
+	if (HW * N * nslabs < 148LL * 4 * pix_per_block) pix_per_block = planes * 4;   // small tensors: more, smaller blocks
+	dim3 g1((unsigned)(((HW + pix_per_block - 1) / pix_per_block) * nslabs), (unsigned)N);
 	size_t smem = groups * 2 * sizeof(float);
 	if (src.dt == DT_F16)
-		gn_stats_kernel<__half><<<g1, threads, smem, s>>>((const __half*)src.ptr, HW, C, cpg, groups, src.st[3], src.st[0], stats, pix_per_block);
+		gn_stats_kernel<__half><<<g1, threads, smem, s>>>((const __half*)src.ptr, HW, C, cpg, groups, src.st[3], src.st[0], stats, pix_per_block, slab_chunks, nslabs);
 	else
-		gn_stats_kernel<float><<<g1, threads, smem, s>>>((const float*)src.ptr, HW, C, cpg, groups, src.st[3], src.st[0], stats, pix_per_block);
+		gn_stats_kernel<float><<<g1, threads, smem, s>>>((const float*)src.ptr, HW, C, cpg, groups, src.st[3], src.st[0], stats, pix_per_block, slab_chunks, nslabs);
 	long long total = HW * (C / 8);
 	dim3 g2((unsigned)std::min<long long>((total + threads - 1) / threads, 148 * 8), (unsigned)N);
 	if (src.dt == DT_F16 && dst.dt == DT_F16)
@@ -395,41 +409,91 @@ void k_groupnorm(cudaStream_t s, const View& dst, const View& src, const float* 
 
 // ------------------------------------------------------------------ LayerNorm (+affine), one warp per row
 // (mlblock_nn.c:58-75; eps 1e-5). Row cached in registers: two exact passes, f32.
-template <typename TI, typename TO, int MAXV>
+// NCH = 8-element chunks per lane (row length <= 256 * NCH); 16-byte loads/stores for f16 rows.
+template <typename TI, typename TO, int NCH>
 __global__ void layernorm_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long rows, int C,
 	long long ld_in, long long ld_out, const float* __restrict__ gamma, const float* __restrict__ beta, float eps)
 {
 	long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
 	if (row >= rows) return;
-	int lane = threadIdx.x & 31;
+	const int lane = threadIdx.x & 31, chunks = C >> 3;
 	const TI* xr = x + row * ld_in;
-	float v[MAXV];
+	float v[NCH][8];
 	float sum = 0.f;
 	#pragma unroll
-	for (int i = 0; i < MAXV; ++i) {
-		int c = lane + i * 32;
-		v[i] = c < C ? (float)xr[c] : 0.f;
-		sum += v[i];
+	for (int i = 0; i < NCH; ++i) {
+		const int ch = lane + i * 32;
+		if (ch < chunks) {
+			if (sizeof(TI) == 2) {
+				uint4 raw = *reinterpret_cast<const uint4*>(xr + ch * 8);
+				const __half2* h = reinterpret_cast<const __half2*>(&raw);
+				#pragma unroll
+				for (int j = 0; j < 4; ++j) { float2 f = __half22float2(h[j]); v[i][2*j] = f.x; v[i][2*j+1] = f.y; }
+			} else {
+				#pragma unroll
+				for (int j = 0; j < 8; ++j) v[i][j] = (float)xr[ch * 8 + j];
+			}
+			#pragma unroll
+			for (int j = 0; j < 8; ++j) sum += v[i][j];
+		}
 	}
 	for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(~0u, sum, o);
-	float mean = sum / C, sq = 0.f;
+	const float mean = sum / C;
+	float sq = 0.f;
 	#pragma unroll
-	for (int i = 0; i < MAXV; ++i) {
-		int c = lane + i * 32;
-		float d = c < C ? v[i] - mean : 0.f;
-		v[i] = d; sq += d * d;
-	}
+	for (int i = 0; i < NCH; ++i)
+		if (lane + i * 32 < chunks) {
+			#pragma unroll
+			for (int j = 0; j < 8; ++j) { v[i][j] -= mean; sq += v[i][j] * v[i][j]; }
+		}
 	for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(~0u, sq, o);
-	float rstd = rsqrtf(sq / C + eps);
+	const float rstd = rsqrtf(sq / C + eps);
 	TO* yr = y + row * ld_out;
 	#pragma unroll
-	for (int i = 0; i < MAXV; ++i) {
-		int c = lane + i * 32;
-		if (c < C) {
-			float t = v[i] * rstd;
-			if (gamma) t = t * gamma[c] + (beta ? beta[c] : 0.f);
-			yr[c] = (TO)t;
+	for (int i = 0; i < NCH; ++i) {
+		const int ch = lane + i * 32;
+		if (ch < chunks) {
+			float t[8];
+			#pragma unroll
+			for (int j = 0; j < 8; ++j) {
+				t[j] = v[i][j] * rstd;
+				if (gamma) t[j] = t[j] * __ldg(gamma + ch * 8 + j) + (beta ? __ldg(beta + ch * 8 + j) : 0.f);
+			}
+			if (sizeof(TO) == 2) {
+				uint4 raw; __half2* h = reinterpret_cast<__half2*>(&raw);
+				#pragma unroll
+				for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(t[2*j], t[2*j+1]);
+				*reinterpret_cast<uint4*>(yr + ch * 8) = raw;
+			} else {
+				#pragma unroll
+				for (int j = 0; j < 8; ++j) yr[ch * 8 + j] = (TO)t[j];
+			}
 		}
+	}
+}
+
+// scalar fallback for row lengths that are not multiples of 8 (or unaligned rows)
+template <typename TI, typename TO>
+__global__ void layernorm_scalar_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long rows, int C,
+	long long ld_in, long long ld_out, const float* __restrict__ gamma, const float* __restrict__ beta, float eps)
+{
+	long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+	if (row >= rows) return;
+	const int lane = threadIdx.x & 31;
+	const TI* xr = x + row * ld_in;
+	float sum = 0.f;
+	for (int c = lane; c < C; c += 32) sum += (float)xr[c];
+	for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(~0u, sum, o);
+	const float mean = sum / C;
+	float sq = 0.f;
+	for (int c = lane; c < C; c += 32) { float d = (float)xr[c] - mean; sq += d * d; }
+	for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(~0u, sq, o);
+	const float rstd = rsqrtf(sq / C + eps);
+	TO* yr = y + row * ld_out;
+	for (int c = lane; c < C; c += 32) {
+		float t = ((float)xr[c] - mean) * rstd;
+		if (gamma) t = t * gamma[c] + (beta ? beta[c] : 0.f);
+		yr[c] = (TO)t;
 	}
 }
 
@@ -439,10 +503,11 @@ static void layernorm_launch(cudaStream_t s, const void* x, void* y, long long r
 {
 	int wpb = 8;
 	unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
-	if (C <= 32 * 24) layernorm_kernel<TI, TO, 24><<<grid, wpb * 32, 0, s>>>((const TI*)x, (TO*)y, rows, C, ldi, ldo, g, b, eps);
-	else if (C <= 32 * 40) layernorm_kernel<TI, TO, 40><<<grid, wpb * 32, 0, s>>>((const TI*)x, (TO*)y, rows, C, ldi, ldo, g, b, eps);
-	else if (C <= 32 * 64) layernorm_kernel<TI, TO, 64><<<grid, wpb * 32, 0, s>>>((const TI*)x, (TO*)y, rows, C, ldi, ldo, g, b, eps);
-	else B200_FATAL("k_layernorm: row length %d too large", C);
+	bool vec = C % 8 == 0 && ldi % 8 == 0 && ldo % 8 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0 && C <= 2048;
+	if (!vec) { layernorm_scalar_kernel<TI, TO><<<grid, wpb * 32, 0, s>>>((const TI*)x, (TO*)y, rows, C, ldi, ldo, g, b, eps); return; }
+	if (C <= 256 * 2) layernorm_kernel<TI, TO, 2><<<grid, wpb * 32, 0, s>>>((const TI*)x, (TO*)y, rows, C, ldi, ldo, g, b, eps);
+	else if (C <= 256 * 5) layernorm_kernel<TI, TO, 5><<<grid, wpb * 32, 0, s>>>((const TI*)x, (TO*)y, rows, C, ldi, ldo, g, b, eps);
+	else layernorm_kernel<TI, TO, 8><<<grid, wpb * 32, 0, s>>>((const TI*)x, (TO*)y, rows, C, ldi, ldo, g, b, eps);
 }
 
 void k_layernorm(cudaStream_t s, const View& dst, const View& src, const float* gamma, const float* beta, float eps)

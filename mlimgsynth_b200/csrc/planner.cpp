@@ -1012,6 +1012,11 @@ static void plan_run_profiled(Plan* P)
 		CUDA_CHECK(cudaEventSynchronize(e1));
 		float ms = 0; CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
 		double fl, by; step_cost(s, &fl, &by);
+		if (env_flag("GGML_B200_PROFILE_STEPS"))
+			fprintf(stderr, "step %-12s kind %2d  %8.1f us  out[%lld,%lld,%lld,%lld] in0[%lld,%lld,%lld,%lld] M%lld N%lld K%lld %s\n", s.name, (int)s.kind, ms * 1e3,
+				(long long)s.out.ne[0], (long long)s.out.ne[1], (long long)s.out.ne[2], (long long)s.out.ne[3],
+				(long long)s.in[0].ne[0], (long long)s.in[0].ne[1], (long long)s.in[0].ne[2], (long long)s.in[0].ne[3],
+				(long long)s.M, (long long)s.N, (long long)s.K, s.atc ? "tc" : "");
 		ProfAcc& a = g_prof[s.kind];
 		a.ms += ms; a.flops += fl; a.bytes += by; a.launches += g_stats.kernel_launches - l0;
 	}
