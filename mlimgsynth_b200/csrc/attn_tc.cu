@@ -65,8 +65,8 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 		:: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-template <int D16MAX>
-__global__ void __launch_bounds__(320, 1)
+template <int D16MAX, int NT>     // NT = query tiles per CTA (2: ping-pong, 320 threads; 1: wide heads, 192 threads)
+__global__ void __launch_bounds__(64 + 128 * NT, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
 	const AttnParams p)
 {
@@ -74,7 +74,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 	uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 	const int tile_bytes = p.dchunks * CHUNK_BYTES;
 	uint8_t* sQ = smem;                                   // [2 tiles]
-	uint8_t* sK = sQ + 2 * tile_bytes;                    // [stages]
+	uint8_t* sK = sQ + NT * tile_bytes;                   // [stages]
 	uint8_t* sV = sK + (size_t)p.stages * tile_bytes;     // [stages]
 	uint64_t* bars = (uint64_t*)(sV + (size_t)p.stages * tile_bytes);
 	uint64_t* q_full = bars;                        // [2]
@@ -89,8 +89,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 	uint32_t* tmem_slot = (uint32_t*)(pv_empty + 2);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int q0 = blockIdx.x * (2 * AQ), h = blockIdx.y, b = blockIdx.z;
-	const int ntile = (q0 + AQ < p.nq) ? 2 : 1;     // the second tile may be entirely out of range
+	const int q0 = blockIdx.x * (NT * AQ), h = blockIdx.y, b = blockIdx.z;
+	const int ntile = (NT == 2 && q0 + AQ < p.nq) ? 2 : 1;     // the second tile may be entirely out of range
 
 	if (threadIdx.x == 0) {
 		tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -208,58 +208,49 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 				const int valid = p.nk - j * AK;      // >= 128 for all but a partial last block
 				mbar_wait(&s_full[t], (uint32_t)j & 1);
 				tc_fence_after();
-				// pass A: row maximum
-				float mx = -INFINITY;
-				if (valid >= AK) {
-					#pragma unroll
-					for (int c = 0; c < 4; ++c) {
-						uint32_t v[32];
-						tmem_ld32(ts + c * 32, v);
-						tmem_ld_wait();
+				// Two passes over the 128 scores of this row (max, then probabilities), 32 columns at a time,
+				// with the next tcgen05.ld always in flight while the current chunk is processed. Four
+				// independent max / sum chains keep the FP pipes busy instead of one serial dependency.
+				uint32_t va[32], vb[32];
+				float mx4[4] = { -INFINITY, -INFINITY, -INFINITY, -INFINITY };
+				float rs4[4] = { 0.f, 0.f, 0.f, 0.f };
+				float m_new = 0.f;
+				const bool full = valid >= AK;
+				auto maxupd = [&](const uint32_t* v, int c) {
+					if (full) {
 						#pragma unroll
-						for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-					}
-				} else {
-					#pragma unroll
-					for (int c = 0; c < 4; ++c) {
-						uint32_t v[32];
-						tmem_ld32(ts + c * 32, v);
-						tmem_ld_wait();
-						#pragma unroll
-						for (int i = 0; i < 32; ++i) if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-					}
-				}
-				const float m_new = fmaxf(m, mx * sl2);
-				const float corr = ex2_approx(m - m_new);      // m = -inf on the first block -> 0
-				// pass B: probabilities, packed to f16 pairs and written over the consumed scores
-				float rowsum = 0.f;
-				#pragma unroll
-				for (int c = 0; c < 4; ++c) {
-					uint32_t v[32];
-					tmem_ld32(ts + c * 32, v);
-					tmem_ld_wait();
-					uint32_t packed[16];
-					if (valid >= AK) {
-						#pragma unroll
-						for (int i = 0; i < 32; i += 2) {
-							float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -m_new));
-							float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sl2, -m_new));
-							rowsum += p0 + p1;
-							__half2 hh = __floats2half2_rn(p0, p1);
-							packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
-						}
+						for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
 					} else {
 						#pragma unroll
-						for (int i = 0; i < 32; i += 2) {
-							float p0 = (c * 32 + i < valid) ? ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -m_new)) : 0.f;
-							float p1 = (c * 32 + i + 1 < valid) ? ex2_approx(fmaf(__uint_as_float(v[i + 1]), sl2, -m_new)) : 0.f;
-							rowsum += p0 + p1;
-							__half2 hh = __floats2half2_rn(p0, p1);
-							packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
-						}
+						for (int i = 0; i < 32; ++i) if (c * 32 + i < valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
+					}
+				};
+				auto proc = [&](const uint32_t* v, int c) {
+					uint32_t packed[16];
+					#pragma unroll
+					for (int i = 0; i < 32; i += 2) {
+						float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -m_new));
+						float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sl2, -m_new));
+						if (!full) { if (c * 32 + i >= valid) p0 = 0.f; if (c * 32 + i + 1 >= valid) p1 = 0.f; }
+						rs4[(i >> 1) & 3] += p0 + p1;
+						__half2 hh = __floats2half2_rn(p0, p1);
+						packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
 					}
 					tmem_st16(ts + c * 16, packed);    // columns [16c, 16c+16) lie inside the already consumed scores
-				}
+				};
+				tmem_ld32(ts, va);
+				tmem_ld_wait(); tmem_ld32(ts + 32, vb); maxupd(va, 0);
+				tmem_ld_wait(); tmem_ld32(ts + 64, va); maxupd(vb, 1);
+				tmem_ld_wait(); tmem_ld32(ts + 96, vb); maxupd(va, 2);
+				tmem_ld_wait(); tmem_ld32(ts, va);      maxupd(vb, 3);
+				const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+				m_new = fmaxf(m, mx * sl2);
+				const float corr = ex2_approx(m - m_new);      // m = -inf on the first block -> 0
+				tmem_ld_wait(); tmem_ld32(ts + 32, vb); proc(va, 0);
+				tmem_ld_wait(); tmem_ld32(ts + 64, va); proc(vb, 1);
+				tmem_ld_wait(); tmem_ld32(ts + 96, vb); proc(va, 2);
+				tmem_ld_wait();                         proc(vb, 3);
+				const float rowsum = (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
 				tmem_st_wait();
 				tc_fence_before();
 				mbar_arrive(&p_full[t]);
@@ -331,7 +322,7 @@ bool attn_tc_supported(const View& o, const View& q, const View& k, const View& 
 {
 	if (causal) return false;
 	int d = (int)q.ne[0];
-	if (d > 128 || d % 8) return false;
+	if (d > 160 || d % 8) return false;
 	if (!operand_ok(q, 0, 1) || !operand_ok(k, 0, 1) || !operand_ok(v, 1, 0)) return false;
 	if (o.dt != DT_F16 || o.st[0] != 1) return false;
 	return true;
@@ -348,10 +339,11 @@ AttnTC* attn_tc_prepare(const View& o, const View& q, const View& k, const View&
 	p.o = o.ptr; p.so_t = o.st[1]; p.so_h = o.st[2]; p.so_b = o.st[3];
 	const size_t tile = (size_t)p.dchunks * CHUNK_BYTES;
 	p.stages = std::max(1, std::min(p.nblk, A_MAX_STAGES));
-	auto total = [&]() { return tile * (2 + 2 * p.stages) + 1024 + 512; };
+	const int nt = p.d16 > 128 ? 1 : 2;
+	auto total = [&]() { return tile * (nt + 2 * p.stages) + 1024 + 512; };
 	while (total() > 220 * 1024 && p.stages > 1) p.stages--;
 	a->smem = total();
-	a->grid = dim3((unsigned)((p.nq + 2 * AQ - 1) / (2 * AQ)), (unsigned)p.H, (unsigned)p.B);
+	a->grid = dim3((unsigned)((p.nq + nt * AQ - 1) / (nt * AQ)), (unsigned)p.H, (unsigned)p.B);
 	bool ok = encode4(&a->tmQ, q.ptr, p.d, p.nq, p.H, p.B, q.st[1], q.st[2], q.st[3]) &&
 	          encode4(&a->tmK, k.ptr, p.d, p.nk, p.H, p.B, k.st[1], k.st[2], k.st[3]) &&
 	          encode4(&a->tmV, v.ptr, p.d, p.nk, p.H, p.B, v.st[0], v.st[2], v.st[3]);   // v is the [nk, d, H, B] view: token stride = st[0]
@@ -363,12 +355,14 @@ void attn_tc_launch(cudaStream_t s, AttnTC* a)
 {
 	static bool attr_set = false;
 	if (!attr_set) {
-		CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-		CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<160, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		attr_set = true;
 	}
-	if (a->p.d16 <= 64) attn_tc_kernel<64><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
-	else attn_tc_kernel<128><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+	if (a->p.d16 <= 64) attn_tc_kernel<64, 2><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+	else if (a->p.d16 <= 128) attn_tc_kernel<128, 2><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+	else attn_tc_kernel<160, 1><<<a->grid, 192, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
 	g_stats.kernel_launches++;
 }
 

@@ -26,6 +26,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;            // 64 f16 = 128 B = one swizzle row
 constexpr int TMEM_COLS = 256;    // accumulator columns allocated per CTA (>= max BN)
 constexpr int MAX_STAGES = 8;
+constexpr int EPI_MAX_IMG = 4;    // per-image epilogue vectors staged in shared memory (tile spans <= 4 images)
 
 struct GemmParams {
 	int M, N, K, num_kb, BN, stages;
@@ -78,6 +79,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 	uint64_t* empty_bar = full_bar + MAX_STAGES;
 	uint64_t* accum_bar = empty_bar + MAX_STAGES;
 	uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+	float* epi_vec = (float*)(tmem_slot + 6);     // [EPI_MAX_IMG][BN] bias + per-image vector, 16-byte aligned
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int n0 = blockIdx.x * p.BN;
@@ -145,9 +147,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 		// ===== epilogue warps 2..5 =====
 		const int quarter = warp & 3;                // TMEM lane quarter this warp may access
 		const int r = quarter * 32 + lane;           // row inside the tile
-		long long grow; bool row_ok;
+		const int et = threadIdx.x - 64;             // 0..127 among the epilogue threads
+		long long grow; bool row_ok; int ii = 0;
 		if (p.conv) {
-			int wi = r % p.bw, hi = (r / p.bw) % p.bh, ii = r / (p.bw * p.bh);
+			int wi = r % p.bw, hi = (r / p.bw) % p.bh; ii = r / (p.bw * p.bh);
 			int w = tw0 + wi, h = th0 + hi, im = ti0 + ii;
 			row_ok = w < p.W && h < p.H && im < p.n_img;
 			grow = ((long long)im * p.H + h) * p.W + w;
@@ -155,13 +158,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 			grow = (long long)m0 + r;
 			row_ok = grow < p.M;
 		}
-		const long long img = p.rowvec ? grow / p.rows_per_image : 0;
+		// While the main loop runs, stage bias (+ the per-image vector) of this tile's columns in shared
+		// memory: the epilogue then never waits on global loads for them.
+		const int n_img_tile = (p.conv && p.rowvec) ? p.bi : 1;
+		const bool staged = n_img_tile <= EPI_MAX_IMG;
+		if (staged) {
+			for (int e = et; e < n_img_tile * p.BN; e += 128) {
+				const int im_l = e / p.BN, c = e - im_l * p.BN, col = n0 + c;
+				float v = 0.f;
+				if (col < p.N) {
+					if (p.bias) v = __ldg(p.bias + col);
+					if (p.rowvec) {
+						const long long im = min((long long)(p.conv ? ti0 + im_l : 0), (long long)p.n_img - 1);
+						const long long o = im * p.rowvec_stride + col;
+						v += p.rowvec_dt == DT_F16 ? __half2float(((const __half*)p.rowvec)[o]) : ((const float*)p.rowvec)[o];
+					}
+				}
+				epi_vec[e] = v;
+			}
+			asm volatile("bar.sync 1, 128;" ::: "memory");     // epilogue warps only
+		}
+		const float* my_vec = epi_vec + (staged ? ii * p.BN : 0);
+		const long long img = (!staged && p.rowvec) ? grow / p.rows_per_image : 0;
+		const bool has_vec = p.bias || p.rowvec;
+
 		mbar_wait(accum_bar, 0);
 		tc_fence_after();
 		const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+		// residual of the next chunk is fetched while the current one is processed
+		const bool res16 = p.residual && p.residual_dt == DT_F16;
+		const __half* rrow = res16 ? (const __half*)p.residual + grow * p.ldr + n0 : nullptr;
+		const bool res_vec = res16 && row_ok && ((((uintptr_t)rrow) & 15) == 0);
+		uint4 rnext[2];
+		auto fetch_res = [&](int c0) {
+			if (res_vec && n0 + c0 + 16 <= p.N) { rnext[0] = *reinterpret_cast<const uint4*>(rrow + c0); rnext[1] = *reinterpret_cast<const uint4*>(rrow + c0 + 8); }
+		};
+		fetch_res(0);
 		for (int c0 = 0; c0 < p.BN; c0 += 16) {
 			uint32_t v[16];
 			tmem_ld16(trow + (uint32_t)c0, v);
+			uint4 rcur[2] = { rnext[0], rnext[1] };
+			if (c0 + 16 < p.BN) fetch_res(c0 + 16);
 			tmem_ld_wait();
 			const int col0 = n0 + c0;
 			if (!row_ok || col0 >= p.N) continue;
@@ -169,15 +206,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 			#pragma unroll
 			for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
 			const bool full = col0 + 16 <= p.N;
-			if (p.bias) {
-				#pragma unroll
-				for (int j = 0; j < 16; ++j) if (full || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
-			}
-			if (p.rowvec) {
-				#pragma unroll
-				for (int j = 0; j < 16; ++j) if (full || col0 + j < p.N) {
-					long long o = img * p.rowvec_stride + col0 + j;
-					f[j] += p.rowvec_dt == DT_F16 ? __half2float(((const __half*)p.rowvec)[o]) : ((const float*)p.rowvec)[o];
+			if (has_vec) {
+				if (staged) {
+					#pragma unroll
+					for (int j = 0; j < 16; j += 4) { float4 t = *reinterpret_cast<const float4*>(my_vec + c0 + j); f[j] += t.x; f[j+1] += t.y; f[j+2] += t.z; f[j+3] += t.w; }
+				} else {
+					#pragma unroll
+					for (int j = 0; j < 16; ++j) if (full || col0 + j < p.N) {
+						if (p.bias) f[j] += __ldg(p.bias + col0 + j);
+						if (p.rowvec) { long long o = img * p.rowvec_stride + col0 + j;
+							f[j] += p.rowvec_dt == DT_F16 ? __half2float(((const __half*)p.rowvec)[o]) : ((const float*)p.rowvec)[o]; }
+					}
 				}
 			}
 			if (p.act != U_NONE) {
@@ -186,15 +225,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 			}
 			if (p.residual) {
 				const long long ro = grow * p.ldr + col0;
-				if (p.residual_dt == DT_F16) {
-					const __half* rp = (const __half*)p.residual + ro;
-					if (full && ((ro & 7) == 0)) {
-						uint4 a = *reinterpret_cast<const uint4*>(rp), b = *reinterpret_cast<const uint4*>(rp + 8);
-						const __half2* ha = reinterpret_cast<const __half2*>(&a); const __half2* hb = reinterpret_cast<const __half2*>(&b);
+				if (res16) {
+					if (res_vec && full) {
+						const __half2* ha = reinterpret_cast<const __half2*>(&rcur[0]); const __half2* hb = reinterpret_cast<const __half2*>(&rcur[1]);
 						#pragma unroll
 						for (int j = 0; j < 4; ++j) { float2 x = __half22float2(ha[j]), y = __half22float2(hb[j]);
 							f[2*j] += x.x; f[2*j+1] += x.y; f[8+2*j] += y.x; f[8+2*j+1] += y.y; }
 					} else {
+						const __half* rp = (const __half*)p.residual + ro;
 						#pragma unroll
 						for (int j = 0; j < 16; ++j) if (full || col0 + j < p.N) f[j] += __half2float(rp[j]);
 					}
@@ -293,7 +331,7 @@ static void finish_setup(GemmTC* g, const GemmEpilogue& ep, int64_t m_tiles, int
 	int stages = (int)std::min<size_t>(MAX_STAGES, (108 * 1024) / stage);
 	stages = std::max(2, std::min(stages, std::max(2, p.num_kb)));
 	p.stages = stages;
-	g->smem = std::max<size_t>(stages * stage + 1024 /*align*/ + (2 * MAX_STAGES + 1) * 8 + 16, 77 * 1024);
+	g->smem = std::max<size_t>(stages * stage + 1024 /*align*/ + (2 * MAX_STAGES + 1) * 8 + 32 + EPI_MAX_IMG * 256 * 4, 77 * 1024);
 	g->grid = dim3((unsigned)((p.N + p.BN - 1) / p.BN), (unsigned)m_tiles);
 	p.bias = ep.bias; p.rowvec = ep.rowvec; p.rowvec_dt = ep.rowvec_dt; p.rowvec_stride = ep.rowvec_stride;
 	p.rows_per_image = ep.rows_per_image > 0 ? ep.rows_per_image : 1;
