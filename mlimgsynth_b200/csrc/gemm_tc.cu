@@ -178,7 +178,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 			}
 			asm volatile("bar.sync 1, 128;" ::: "memory");     // epilogue warps only
 		}
-		const float* my_vec = epi_vec + (staged ? ii * p.BN : 0);
+		const float* my_vec = epi_vec + ((staged && n_img_tile > 1) ? ii * p.BN : 0);
 		const long long img = (!staged && p.rowvec) ? grow / p.rows_per_image : 0;
 		const bool has_vec = p.bias || p.rowvec;
 
