@@ -23,6 +23,7 @@
 #include "kernels.h"
 #include "tc_common.cuh"
 #include <algorithm>
+#include <type_traits>
 
 namespace b200 {
 
@@ -34,10 +35,15 @@ constexpr int A_TMEM_COLS = 512;
 constexpr int A_MAX_STAGES = 4;
 
 struct AttnParams {
-	int d, d16, dchunks, nq, nk, H, B, stages, nblk;
+	int d, d16, dchunks, nq, nk, H, B, stages, nblk, pingpong;
 	float scale_log2;
 	void* o; long long so_t, so_h, so_b;
+	long long* trace;     // debug timeline (tools/attn_trace.cu); null in production
 };
+// Timeline events of CTA (0,0,0): slot = role * 64 * 8 + j * 8 + ev, roles 0/1 = softmax warp of tile a/b (lane 0 of its
+// first warp), 2 = the MMA thread.
+#define ATTN_TR(role, j, ev) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 64) \
+	p.trace[((role) * 64 + (j)) * 8 + (ev)] = clock64(); } while (0)
 
 struct AttnTC {
 	CUtensorMap tmQ, tmK, tmV;
@@ -48,6 +54,12 @@ struct AttnTC {
 
 __device__ __forceinline__ float ex2_approx(float x)
 { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+__device__ __forceinline__ float max3f(float a, float b, float c)
+{ float y; asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c)); return y; }
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r)
 {
@@ -73,7 +85,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 	extern __shared__ __align__(1024) uint8_t smem_raw[];
 	uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 	const int tile_bytes = p.dchunks * CHUNK_BYTES;
-	uint8_t* sQ = smem;                                   // [2 tiles]
+	uint8_t* sQ = smem;                                   // [NT tiles]
 	uint8_t* sK = sQ + NT * tile_bytes;                   // [stages]
 	uint8_t* sV = sK + (size_t)p.stages * tile_bytes;     // [stages]
 	uint64_t* bars = (uint64_t*)(sV + (size_t)p.stages * tile_bytes);
@@ -85,27 +97,28 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 	uint64_t* s_full = v_empty + A_MAX_STAGES;      // [2 tiles]  QK done
 	uint64_t* p_full = s_full + 2;                  // [2 tiles]  probabilities written (128 arrivals)
 	uint64_t* pv_full = p_full + 2;                 // [2 tiles]  PV done
-	uint64_t* pv_empty = pv_full + 2;               // [2 tiles]  PV tile consumed (128 arrivals)
-	uint32_t* tmem_slot = (uint32_t*)(pv_empty + 2);
+	uint32_t* tmem_slot = (uint32_t*)(pv_full + 2);
 
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
 	const int q0 = blockIdx.x * (NT * AQ), h = blockIdx.y, b = blockIdx.z;
 	const int ntile = (NT == 2 && q0 + AQ < p.nq) ? 2 : 1;     // the second tile may be entirely out of range
+	constexpr uint32_t O_BASE = NT * 128;                      // TMEM: S_t at t*128 (P_t aliases its first 64 columns), O_t behind them
+	constexpr uint32_t O_STRIDE = NT == 2 ? 128 : 256;
 
 	if (threadIdx.x == 0) {
 		tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
 		for (int s = 0; s < p.stages; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-		for (int t = 0; t < 2; ++t) { mbar_init(&q_full[t], 1); mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 128); mbar_init(&pv_full[t], 1); mbar_init(&pv_empty[t], 128); }
+		for (int t = 0; t < 2; ++t) { mbar_init(&q_full[t], 1); mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 128); mbar_init(&pv_full[t], 1); }
 		fence_barrier_init();
 	}
-	if (warp == 1) tmem_alloc(tmem_slot, A_TMEM_COLS);
+	constexpr int W_TMA = NT * 4, W_MMA = NT * 4 + 1;     // the issuing warps have the HIGHEST warp ids: the SM's arbiter favours them
+	if (warp == W_MMA) tmem_alloc(tmem_slot, A_TMEM_COLS);
 	tc_fence_before();
 	__syncthreads();
 	tc_fence_after();
-	const uint32_t tmem_base = *tmem_slot;
-	// TMEM columns: S_a [0,128) (P_a aliases [0,64)), S_b [128,256), O_a tile [256,384), O_b tile [384,512)
+	const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
-	if (warp == 0) {
+	if (warp == W_TMA) {
 		if (lane == 0) {
 			for (int t = 0; t < ntile; ++t) {
 				mbar_expect_tx(&q_full[t], tile_bytes);
@@ -121,162 +134,215 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 				for (int c = 0; c < p.dchunks; ++c) tma_load_4d(sV + (size_t)s * tile_bytes + c * CHUNK_BYTES, &tmV, &v_full[s], c * ACH, j * AK, h, b);
 			}
 		}
-	} else if (warp == 1) {
-		if (lane == 0) {
-			const uint32_t idesc_qk = make_idesc_f16(AQ, AK, 0, 0);
-			const uint32_t idesc_pv = make_idesc_f16(AQ, p.d16, 0, 1);     // A = P (TMEM), B = V MN-major ([key][d], d contiguous)
-			auto issue_qk = [&](int t, int j) {
-				const int s = j % p.stages;
-				if (t == 0) { mbar_wait(&k_full[s], (uint32_t)(j / p.stages) & 1); tc_fence_after(); }
-				const uint32_t q_addr = smem_u32(sQ + t * tile_bytes);
-				const uint32_t k_addr = smem_u32(sK + (size_t)s * tile_bytes);
-				int first = 1;
-				for (int c = 0; c < p.dchunks; ++c)
-					for (int kk = 0; kk < 4; ++kk) {
-						if (c * ACH + kk * 16 >= p.d16) break;
-						uint64_t ad = make_smem_desc_sw128(q_addr + c * CHUNK_BYTES + kk * 32, 16, 1024);
-						uint64_t bd = make_smem_desc_sw128(k_addr + c * CHUNK_BYTES + kk * 32, 16, 1024);
-						umma_f16(tmem_base + t * 128, ad, bd, idesc_qk, first ? 0u : 1u);
-						first = 0;
-					}
+	} else if (warp == W_MMA) {
+		// ===== MMA issuer: the whole warp runs the (warp-uniform) control flow and the barrier waits, one elected
+		// lane issues the tcgen05 instructions, so descriptors and addresses stay in uniform registers.
+		const uint32_t idesc_qk = make_idesc_f16(AQ, AK, 0, 0);
+		const uint32_t idesc_pv = make_idesc_f16(AQ, p.d16, 0, 1);     // A = P (TMEM), B = V MN-major ([key][d], d contiguous)
+		// Descriptors are built once; per MMA only a constant is added (16 columns = 32 B = +2 in the 16-byte
+		// address field; the next 64-column chunk is CHUNK_BYTES further).
+		const uint64_t qdesc0 = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+		const uint64_t kdesc0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+		const uint64_t vdesc0 = make_smem_desc_sw128(smem_u32(sV), CHUNK_BYTES, 1024);
+		const uint32_t tile16 = (uint32_t)tile_bytes >> 4;
+		const int nk16 = p.d16 >> 4;
+		auto issue_qk = [&](int t, int j) {
+			const int s = j % p.stages;
+			if (t == 0) mbar_wait(&k_full[s], (uint32_t)(j / p.stages) & 1);
+			tc_fence_after();
+			if (elect_one()) {
+				const uint64_t ad = qdesc0 + (uint64_t)(t * tile16), bd = kdesc0 + (uint64_t)(s * tile16);
+				const uint32_t td = tmem_base + t * 128;
+				#pragma unroll
+				for (int kk = 0; kk < D16MAX / 16; ++kk) {      // unrolled: every offset is an immediate
+					const uint32_t off = (uint32_t)((kk >> 2) * (CHUNK_BYTES >> 4) + (kk & 3) * 2);
+					if (kk < nk16) umma_f16(td, ad + off, bd + off, idesc_qk, kk ? 1u : 0u);
+				}
 				umma_commit(&s_full[t]);
 				if (t == ntile - 1) umma_commit(&k_empty[s]);
-			};
-			auto issue_pv = [&](int t, int j) {
-				const int s = j % p.stages;
-				if (t == 0) mbar_wait(&v_full[s], (uint32_t)(j / p.stages) & 1);
-				mbar_wait(&p_full[t], (uint32_t)j & 1);
-				mbar_wait(&pv_empty[t], ((uint32_t)j & 1) ^ 1);
-				tc_fence_after();
-				const uint32_t v_addr = smem_u32(sV + (size_t)s * tile_bytes);
-				const int valid = min(AK, p.nk - j * AK);
-				int first = 1;
-				for (int kk = 0; kk < AK / 16; ++kk) {
-					const int key = kk * 16;
-					if (key >= valid) break;
-					// V tile: rows = keys (128 B each), 8-row swizzle atoms 1024 B apart (SBO), next 64 d-columns CHUNK_BYTES away (LBO)
-					uint64_t bd = make_smem_desc_sw128(v_addr + key * 128, CHUNK_BYTES, 1024);
-					// P in tensor memory: 16 keys = 8 packed 32-bit columns per k-step
-					umma_f16_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + kk * 8, bd, idesc_pv, first ? 0u : 1u);
-					first = 0;
-				}
+				ATTN_TR(2, j, t * 4 + 3);
+			}
+			__syncwarp();
+		};
+		// O_t += P_t V, accumulated IN TENSOR MEMORY over all key blocks (the softmax warps rescale it in
+		// place on the rare blocks where the running maximum moves by more than 2^8)
+		auto issue_pv = [&](int t, int j) {
+			const int s = j % p.stages;
+			if (t == 0) mbar_wait(&v_full[s], (uint32_t)(j / p.stages) & 1);
+			mbar_wait(&p_full[t], (uint32_t)j & 1);
+			tc_fence_after();
+			if (elect_one()) {
+				ATTN_TR(2, j, t * 4 + 1);
+				// V tile: rows = keys (128 B each), 8-row swizzle atoms 1024 B apart (SBO), next 64 d-columns CHUNK_BYTES
+				// away (LBO); 16 keys further = +16*128 B. P in tensor memory: 16 keys = 8 packed 32-bit columns.
+				const uint64_t bd = vdesc0 + (uint64_t)(s * tile16);
+				const uint32_t td = tmem_base + O_BASE + t * O_STRIDE, ta = tmem_base + t * 128;
+				const int nkk = (min(AK, p.nk - j * AK) + 15) >> 4;
+				#pragma unroll
+				for (int kk = 0; kk < AK / 16; ++kk)
+					if (kk < nkk) umma_f16_ts(td, ta + kk * 8, bd + (uint64_t)(kk * 128), idesc_pv, (j | kk) ? 1u : 0u);
 				umma_commit(&pv_full[t]);
 				if (t == ntile - 1) umma_commit(&v_empty[s]);
-			};
-			for (int t = 0; t < ntile; ++t) { mbar_wait(&q_full[t], 0); }
-			for (int t = 0; t < ntile; ++t) issue_qk(t, 0);
-			for (int j = 0; j < p.nblk; ++j) {
-				for (int t = 0; t < ntile; ++t) {
-					issue_pv(t, j);                             // in-order after it: S_t/P_t may be overwritten
-					if (j + 1 < p.nblk) issue_qk(t, j + 1);
-				}
+				ATTN_TR(2, j, t * 4 + 2);
+			}
+			__syncwarp();
+		};
+		for (int t = 0; t < ntile; ++t) { mbar_wait(&q_full[t], 0); }
+		for (int t = 0; t < ntile; ++t) issue_qk(t, 0);
+		for (int j = 0; j < p.nblk; ++j) {
+			for (int t = 0; t < ntile; ++t) {
+				issue_pv(t, j);                             // in-order after it: S_t/P_t may be overwritten
+				if (j + 1 < p.nblk) issue_qk(t, j + 1);
 			}
 		}
 	} else {
-		// ===== softmax + accumulate: group 0 = warps 2..5 (tile a), group 1 = warps 6..9 (tile b) =====
-		const int t = (warp - 2) >> 2;
+		// ===== softmax: group 0 = warps 0..3 (tile a), group 1 = warps 4..7 (tile b); one query row per thread =====
+		const int t = warp >> 2;
 		if (t < ntile) {
 			const int quarter = warp & 3;
 			const int r = quarter * 32 + lane;
 			const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-			const uint32_t ts = tmem_base + t * 128 + lane_off;           // scores / probabilities of this row
-			const uint32_t tpv = tmem_base + 256 + t * 128 + lane_off;    // PV tile of this row
+			const uint32_t ts = tmem_base + t * 128 + lane_off;                     // scores / probabilities of this row
+			const uint32_t to = tmem_base + O_BASE + t * O_STRIDE + lane_off;       // output accumulator of this row
 			const float sl2 = p.scale_log2;
-			float m = -INFINITY, l = 0.f, corr_saved = 0.f;
-			float acc[D16MAX];
-			#pragma unroll
-			for (int i = 0; i < D16MAX; ++i) acc[i] = 0.f;
+			float m = -INFINITY, l = 0.f;     // running (possibly stale) maximum in the exp2 domain, running sum
+			const bool pingpong = NT == 2 && ntile == 2 && p.pingpong;
+			const bool tr = quarter == 0 && lane == 0;     // first warp of the group
+			if (pingpong && t == 1) named_bar_arrive(2, 256);      // tile a takes the first turn
 
-			auto accumulate = [&](int jj, float corr) {
-				mbar_wait(&pv_full[t], (uint32_t)jj & 1);
-				tc_fence_after();
-				#pragma unroll
-				for (int c0 = 0; c0 < D16MAX; c0 += 16) {
-					if (c0 < p.d16) {
-						uint32_t v[16];
-						tmem_ld16(tpv + c0, v);
-						tmem_ld_wait();
-						#pragma unroll
-						for (int i = 0; i < 16; ++i) acc[c0 + i] = fmaf(acc[c0 + i], corr, __uint_as_float(v[i]));
-					}
-				}
-				tc_fence_before();
-				mbar_arrive(&pv_empty[t]);
-			};
-
-			for (int j = 0; j < p.nblk; ++j) {
-				const int valid = p.nk - j * AK;      // >= 128 for all but a partial last block
+			// One key block: two passes over the 128 scores of this row (max, then probabilities), 32 columns
+			// at a time, the next tcgen05.ld always in flight while the current chunk is processed. FULL is a
+			// compile-time tag so that the common full block carries no per-element masking (ISETP/FSEL).
+			auto block = [&](int j, auto full_tag) {
+				constexpr bool FULL = decltype(full_tag)::value;
+				const int valid = p.nk - j * AK;
+				if (tr) ATTN_TR(t, j, 0);
 				mbar_wait(&s_full[t], (uint32_t)j & 1);
 				tc_fence_after();
-				// Two passes over the 128 scores of this row (max, then probabilities), 32 columns at a time,
-				// with the next tcgen05.ld always in flight while the current chunk is processed. Four
-				// independent max / sum chains keep the FP pipes busy instead of one serial dependency.
+				if (tr) ATTN_TR(t, j, 1);
 				uint32_t va[32], vb[32];
 				float mx4[4] = { -INFINITY, -INFINITY, -INFINITY, -INFINITY };
 				float rs4[4] = { 0.f, 0.f, 0.f, 0.f };
-				float m_new = 0.f;
-				const bool full = valid >= AK;
 				auto maxupd = [&](const uint32_t* v, int c) {
-					if (full) {
+					if (FULL) {
 						#pragma unroll
-						for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
+						for (int i = 0; i < 32; i += 8) {      // 3-input max (FMNMX3): half the ALU-pipe work
+							mx4[0] = max3f(mx4[0], __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+							mx4[1] = max3f(mx4[1], __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+							mx4[2] = max3f(mx4[2], __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+							mx4[3] = max3f(mx4[3], __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
+						}
 					} else {
 						#pragma unroll
 						for (int i = 0; i < 32; ++i) if (c * 32 + i < valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
 					}
-				};
-				auto proc = [&](const uint32_t* v, int c) {
-					uint32_t packed[16];
-					#pragma unroll
-					for (int i = 0; i < 32; i += 2) {
-						float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -m_new));
-						float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sl2, -m_new));
-						if (!full) { if (c * 32 + i >= valid) p0 = 0.f; if (c * 32 + i + 1 >= valid) p1 = 0.f; }
-						rs4[(i >> 1) & 3] += p0 + p1;
-						__half2 hh = __floats2half2_rn(p0, p1);
-						packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
-					}
-					tmem_st16(ts + c * 16, packed);    // columns [16c, 16c+16) lie inside the already consumed scores
 				};
 				tmem_ld32(ts, va);
 				tmem_ld_wait(); tmem_ld32(ts + 32, vb); maxupd(va, 0);
 				tmem_ld_wait(); tmem_ld32(ts + 64, va); maxupd(vb, 1);
 				tmem_ld_wait(); tmem_ld32(ts + 96, vb); maxupd(va, 2);
 				tmem_ld_wait(); tmem_ld32(ts, va);      maxupd(vb, 3);
-				const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-				m_new = fmaxf(m, mx * sl2);
-				const float corr = ex2_approx(m - m_new);      // m = -inf on the first block -> 0
-				tmem_ld_wait(); tmem_ld32(ts + 32, vb); proc(va, 0);
-				tmem_ld_wait(); tmem_ld32(ts + 64, va); proc(vb, 1);
-				tmem_ld_wait(); tmem_ld32(ts + 96, vb); proc(va, 2);
-				tmem_ld_wait();                         proc(vb, 3);
-				const float rowsum = (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+				const float m_blk = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sl2;
+				// Lazy rescaling: keep the old maximum while the block maximum exceeds it by < 2^8 (p <= 256 is
+				// exact enough in f16 and cannot overflow the f32 sums); otherwise move it and rescale O and l.
+				if (j == 0) m = m_blk;
+				else {
+					const bool need = m_blk > m + 8.0f;
+					if (__any_sync(0xffffffffu, need)) {
+						const float m_new = need ? m_blk : m;
+						const float corr = ex2_approx(m - m_new);
+						m = m_new;
+						l *= corr;
+						mbar_wait(&pv_full[t], (uint32_t)(j - 1) & 1);     // all PV products so far have landed in O
+						tc_fence_after();
+						#pragma unroll
+						for (int c0 = 0; c0 < D16MAX; c0 += 16) {
+							if (c0 < p.d16) {
+								uint32_t o[16];
+								tmem_ld16(to + c0, o);
+								tmem_ld_wait();
+								#pragma unroll
+								for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+								tmem_st16(to + c0, o);
+							}
+						}
+					}
+				}
+				// Ping-pong: the exp pass (MUFU-bound) of the two tiles strictly alternates, so one tile's
+				// QK/PV products and max pass run under the other tile's exponentials instead of both tiles
+				// contending for the MUFU in lockstep and then idling together while the tensor core works.
+				if (tr) ATTN_TR(t, j, 2);
+				if (pingpong) named_bar_sync(2 + t, 256);
+				if (tr) ATTN_TR(t, j, 3);
+				const float mneg = -m;
+				// Exp pass, software-pipelined over the four 32-column chunks with three register buffers: the
+				// exponentials (FFMA + MUFU.EX2, in place) of chunk c+1 are issued BEFORE the sum / f16 pack /
+				// tcgen05.st of chunk c, so the MUFU stream never drains at a chunk boundary.
+				uint32_t vc[32];
+				auto exps = [&](uint32_t* v, int c) {
+					#pragma unroll
+					for (int i = 0; i < 32; ++i) {
+						float e = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, mneg));
+						if (!FULL) { if (c * 32 + i >= valid) e = 0.f; }
+						v[i] = __float_as_uint(e);
+					}
+				};
+				auto finish = [&](const uint32_t* v, int c) {
+					uint32_t packed[16];
+					#pragma unroll
+					for (int i = 0; i < 32; i += 2) {
+						const float p0 = __uint_as_float(v[i]), p1 = __uint_as_float(v[i + 1]);
+						rs4[(i >> 1) & 3] += p0 + p1;
+						__half2 hh = __floats2half2_rn(p0, p1);
+						packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+					}
+					tmem_st16(ts + c * 16, packed);    // columns [16c, 16c+16) lie inside scores that were already read
+				};
+				tmem_ld_wait(); tmem_ld32(ts + 32, vb); exps(va, 0);
+				tmem_ld_wait(); tmem_ld32(ts + 64, vc); exps(vb, 1); finish(va, 0);
+				tmem_ld_wait(); tmem_ld32(ts + 96, va); exps(vc, 2); finish(vb, 1);
+				tmem_ld_wait();                         exps(va, 3); finish(vc, 2);
+				finish(va, 3);
+				if (tr) ATTN_TR(t, j, 4);
+				if (pingpong && (t == 0 || j + 1 < p.nblk)) named_bar_arrive(2 + (t ^ 1), 256);
+				l += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
 				tmem_st_wait();
 				tc_fence_before();
 				mbar_arrive(&p_full[t]);
-				l = fmaf(l, corr, rowsum);
-				m = m_new;
-				if (j > 0) accumulate(j - 1, corr_saved);
-				corr_saved = corr;
-			}
-			accumulate(p.nblk - 1, corr_saved);
+				if (tr) ATTN_TR(t, j, 5);
+			};
+			const int nfull = p.nk / AK;      // a partial block can only be the last one
+			for (int j = 0; j < nfull; ++j) block(j, std::true_type{});
+			if (nfull < p.nblk) block(nfull, std::false_type{});
 
+			// epilogue: O / l, written token-major ([token][head][d]) for the output projection GEMM
+			mbar_wait(&pv_full[t], (uint32_t)(p.nblk - 1) & 1);
+			tc_fence_after();
 			const long long tok = (long long)q0 + t * AQ + r;
-			if (tok < p.nq) {
-				const float inv = l > 0.f ? 1.0f / l : 0.f;
-				__half* op = (__half*)p.o + tok * p.so_t + (long long)h * p.so_h + (long long)b * p.so_b;
-				const bool vec = ((((uintptr_t)op) & 15) == 0);
-				#pragma unroll
-				for (int c0 = 0; c0 < D16MAX; c0 += 8) {
-					if (c0 < p.d) {
-						if (vec && c0 + 8 <= p.d) {
-							uint4 o4; __half2* hp = reinterpret_cast<__half2*>(&o4);
-							#pragma unroll
-							for (int i = 0; i < 4; ++i) hp[i] = __floats2half2_rn(acc[c0 + 2 * i] * inv, acc[c0 + 2 * i + 1] * inv);
-							*reinterpret_cast<uint4*>(op + c0) = o4;
-						} else {
-							#pragma unroll
-							for (int i = 0; i < 8; ++i) if (c0 + i < p.d) op[c0 + i] = __float2half_rn(acc[c0 + i] * inv);
+			const float inv = l > 0.f ? 1.0f / l : 0.f;
+			__half* op = (__half*)p.o + tok * p.so_t + (long long)h * p.so_h + (long long)b * p.so_b;
+			const bool vec = ((((uintptr_t)op) & 15) == 0);
+			#pragma unroll
+			for (int c0 = 0; c0 < D16MAX; c0 += 16) {
+				if (c0 < p.d16) {
+					uint32_t o[16];
+					tmem_ld16(to + c0, o);
+					tmem_ld_wait();
+					if (tok < p.nq) {
+						#pragma unroll
+						for (int h8 = 0; h8 < 16; h8 += 8) {
+							const int cc = c0 + h8;
+							if (cc < p.d) {
+								if (vec && cc + 8 <= p.d) {
+									uint4 o4; __half2* hp = reinterpret_cast<__half2*>(&o4);
+									#pragma unroll
+									for (int i = 0; i < 4; ++i) hp[i] = __floats2half2_rn(__uint_as_float(o[h8 + 2 * i]) * inv, __uint_as_float(o[h8 + 2 * i + 1]) * inv);
+									*reinterpret_cast<uint4*>(op + cc) = o4;
+								} else {
+									#pragma unroll
+									for (int i = 0; i < 8; ++i) if (cc + i < p.d) op[cc + i] = __float2half_rn(__uint_as_float(o[h8 + i]) * inv);
+								}
+							}
 						}
 					}
 				}
@@ -285,7 +351,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 	}
 	tc_fence_before();
 	__syncthreads();
-	if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, A_TMEM_COLS); }
+	if (warp == W_MMA) { tc_fence_after(); tmem_dealloc(tmem_base, A_TMEM_COLS); }
 }
 
 // ------------------------------------------------------------------ host
@@ -332,6 +398,8 @@ AttnTC* attn_tc_prepare(const View& o, const View& q, const View& k, const View&
 {
 	AttnTC* a = new AttnTC();
 	AttnParams& p = a->p;
+	p.trace = nullptr;
+	{ const char* e = getenv("GGML_B200_ATTN_PP"); p.pingpong = e ? atoi(e) : 1; }
 	p.d = (int)q.ne[0]; p.d16 = (p.d + 15) / 16 * 16; p.dchunks = (p.d + ACH - 1) / ACH;
 	p.nq = (int)q.ne[1]; p.nk = (int)k.ne[1]; p.H = (int)q.ne[2]; p.B = (int)q.ne[3];
 	p.nblk = (p.nk + AK - 1) / AK;
@@ -367,5 +435,6 @@ void attn_tc_launch(cudaStream_t s, AttnTC* a)
 }
 
 void attn_tc_free(AttnTC* a) { delete a; }
+void attn_tc_set_trace(AttnTC* a, long long* dev_buf) { a->p.trace = dev_buf; }
 
 }  // namespace b200

@@ -40,6 +40,7 @@ bool    attn_tc_supported(const View& o, const View& q, const View& k, const Vie
 AttnTC* attn_tc_prepare(const View& o, const View& q, const View& k, const View& v, float scale);
 void    attn_tc_launch(cudaStream_t s, AttnTC* a);
 void    attn_tc_free(AttnTC* a);
+void    attn_tc_set_trace(AttnTC* a, long long* dev_buf);   // debug timeline of CTA 0 (tools/attn_trace.cu)
 
 // ---- tensor-core GEMM / implicit conv (gemm_tc.cu)
 struct GemmEpilogue {

@@ -34,6 +34,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 		}
 	}
 }
+// One lane of a converged warp (warp-uniform control flow around it keeps descriptors in uniform registers).
+__device__ __forceinline__ bool elect_one()
+{
+	uint32_t pred;
+	asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+	return pred != 0;
+}
+__device__ __forceinline__ int warp_id_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t x) { return __shfl_sync(0xffffffffu, x, 0); }
+
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
