@@ -37,13 +37,15 @@ struct GemmParams {
 	const void* rowvec; int rowvec_dt; long long rowvec_stride; long long rows_per_image;
 	const void* residual; int residual_dt; long long ldr;
 	int act;
+	int m_tiles, n_tiles, num_tiles;   // persistent kernel: static tile schedule
 };
 
 struct GemmTC {
-	CUtensorMap tmA, tmB;
+	CUtensorMap tmA, tmB, tmC, tmR;     // tmC / tmR: output store / residual load maps of the persistent kernel
 	GemmParams p;
 	dim3 grid;
 	size_t smem;
+	bool persistent = false;
 };
 
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row swizzle atoms 1024 B apart.
@@ -271,6 +273,238 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 	if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
+// ------------------------------------------------------------------ the persistent kernel (v2)
+// One CTA per SM walks a static list of output tiles (n fastest, so CTAs of a wave share activation rows in L2):
+//   warps 0..3  epilogue (TMEM lane quarter = warp id): accumulator -> registers (tcgen05.ld) -> + bias / per-image
+//               vector (staged in shared memory), activation, + residual (TMA-loaded into the staging tile) ->
+//               f16 -> 64B-swizzled staging tile -> TMA store. Global traffic of the epilogue is bulk-async only.
+//   warp 4      TMA producer, warp 5 MMA issuer: both run warp-uniform control flow with one elected lane issuing,
+//               so descriptors live in uniform registers (no R2UR per instruction); highest warp ids = issue priority.
+// The accumulator is double-buffered in tensor memory (2 x 256 columns): the epilogue of tile i overlaps the main
+// loop of tile i+1, and barrier setup / TMEM allocation / descriptor prefetch happen once per SM, not per tile.
+constexpr int P_THREADS = 192;
+constexpr int P_EPI_MAX_IMG = 8;
+constexpr int STG_CHUNK_COLS = 32;                        // staging chunk: [128 rows][32 f16] = 8 KB, SWIZZLE_64B
+constexpr int STG_CHUNK_BYTES = BM * STG_CHUNK_COLS * 2;
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* src, int c0, int c1)
+{
+	asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+		:: "l"(tm), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2, int c3)
+{
+	asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+		:: "l"(tm), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__global__ void __launch_bounds__(P_THREADS, 1)
+gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+	const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmParams p)
+{
+	extern __shared__ __align__(1024) uint8_t smem_raw[];
+	uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+	const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)p.BN * BK * 2, stage_bytes = a_bytes + b_bytes;
+	const int n_chunks = (p.BN + STG_CHUNK_COLS - 1) / STG_CHUNK_COLS;
+	uint8_t* stg = smem + (size_t)p.stages * stage_bytes;                       // staging tile (1024-aligned)
+	float* epi_vec = (float*)(stg + (size_t)n_chunks * STG_CHUNK_BYTES);        // [P_EPI_MAX_IMG][BN]
+	uint64_t* full_bar  = (uint64_t*)(epi_vec + P_EPI_MAX_IMG * 256);
+	uint64_t* empty_bar = full_bar + MAX_STAGES;
+	uint64_t* acc_full  = empty_bar + MAX_STAGES;      // [2]
+	uint64_t* acc_empty = acc_full + 2;                // [2]
+	uint64_t* res_full  = acc_empty + 2;               // [1]
+	uint32_t* tmem_slot = (uint32_t*)(res_full + 1);
+
+	const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
+	if (threadIdx.x == 0) {
+		tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmC);
+		if (p.residual) tma_prefetch_desc(&tmR);
+		for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+		for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+		mbar_init(res_full, 1);
+		fence_barrier_init();
+	}
+	if (warp == 5) tmem_alloc(tmem_slot, 512);
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = uniform_u32(*tmem_slot);
+
+	// tile id -> coordinates (n fastest)
+	auto tile_coords = [&](int tile, int& n0, int& m0, int& tw0, int& th0, int& ti0) {
+		const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+		n0 = nt * p.BN; m0 = mt * BM; tw0 = th0 = ti0 = 0;
+		if (p.conv) {
+			const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, ti = mt / (p.tiles_w * p.tiles_h);
+			tw0 = tw * p.bw; th0 = th * p.bh; ti0 = ti * p.bi;
+		}
+	};
+
+	if (warp == 4) {
+		// ===== TMA producer =====
+		const int cpt = p.conv ? p.Cin / BK : 1;          // channel chunks per filter tap
+		int s = 0; uint32_t ph = 0;                        // ring slot and its phase, carried across tiles (no division in the loop)
+		for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+			int n0, m0, tw0, th0, ti0; tile_coords(tile, n0, m0, tw0, th0, ti0);
+			int tap = 0, cc = 0;
+			for (int kb = 0; kb < p.num_kb; ++kb) {
+				mbar_wait(&empty_bar[s], ph ^ 1);
+				if (elect_one()) {
+					uint8_t* sa = smem + (size_t)s * stage_bytes;
+					mbar_expect_tx(&full_bar[s], stage_bytes);
+					if (p.conv) {
+						const int kh = (tap * 11) >> 5, kw = tap - kh * 3;      // tap / 3 for tap < 9
+						tma_load_4d(sa, &tmA, &full_bar[s], cc * BK, tw0 + kw - 1, th0 + kh - 1, ti0);
+					} else {
+						tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m0);
+					}
+					tma_load_2d(sa + a_bytes, &tmB, &full_bar[s], kb * BK, n0);
+				}
+				__syncwarp();
+				if (++cc == cpt) { cc = 0; ++tap; }
+				if (++s == p.stages) { s = 0; ph ^= 1; }
+			}
+		}
+	} else if (warp == 5) {
+		// ===== MMA issuer =====
+		const uint32_t idesc = make_idesc(p.BN);
+		const uint64_t adesc0 = make_smem_desc(smem_u32(smem)), bdesc0 = make_smem_desc(smem_u32(smem) + a_bytes);
+		const uint32_t stage16 = stage_bytes >> 4;
+		int s = 0; uint32_t ph = 0, lt = 0;                // ring slot / phase, local tile counter
+		for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+			const uint32_t buf = lt & 1;
+			mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);       // epilogue drained this accumulator
+			tc_fence_after();
+			const uint32_t td = tmem_base + buf * 256;
+			for (int kb = 0; kb < p.num_kb; ++kb) {
+				mbar_wait(&full_bar[s], ph);
+				tc_fence_after();
+				if (elect_one()) {
+					const uint64_t ad = adesc0 + (uint64_t)(s * stage16), bd = bdesc0 + (uint64_t)(s * stage16);
+					#pragma unroll
+					for (int k = 0; k < BK / 16; ++k)
+						umma_f16(td, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+					umma_commit(&empty_bar[s]);
+					if (kb == p.num_kb - 1) umma_commit(&acc_full[buf]);
+				}
+				__syncwarp();
+				if (++s == p.stages) { s = 0; ph ^= 1; }
+			}
+		}
+	} else {
+		// ===== epilogue warps 0..3 =====
+		const int r = warp * 32 + lane;                    // row of the tile = TMEM lane
+		const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+		const uint32_t row_sw = (uint32_t)((r >> 1) & 3);  // SWIZZLE_64B: 16-byte unit index ^= address bits [7,8]
+		uint8_t* my_row = stg + r * 64;
+		const bool has_vec = p.bias || p.rowvec;
+		const int n_img_tile = (p.conv && p.rowvec) ? p.bi : 1;
+		const int ii = p.conv ? r / (p.bw * p.bh) : 0;     // image of this row inside the tile
+		auto issue_res_load = [&](int tile) {              // one thread: residual tile -> staging
+			int n0, m0, tw0, th0, ti0; tile_coords(tile, n0, m0, tw0, th0, ti0);
+			mbar_expect_tx(res_full, (uint32_t)n_chunks * STG_CHUNK_BYTES);
+			for (int c = 0; c < n_chunks; ++c) {
+				if (p.conv) tma_load_4d(stg + c * STG_CHUNK_BYTES, &tmR, res_full, n0 + c * STG_CHUNK_COLS, tw0, th0, ti0);
+				else tma_load_2d(stg + c * STG_CHUNK_BYTES, &tmR, res_full, n0 + c * STG_CHUNK_COLS, m0);
+			}
+		};
+		if (p.residual && threadIdx.x == 0 && (int)blockIdx.x < p.num_tiles) issue_res_load(blockIdx.x);
+		uint32_t lt = 0;
+		for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+			int n0, m0, tw0, th0, ti0; tile_coords(tile, n0, m0, tw0, th0, ti0);
+			const uint32_t buf = lt & 1;
+			// stage bias (+ per-image vector) of this tile's columns; the previous store must have left the staging tile
+			if (has_vec) {
+				for (int e = threadIdx.x; e < n_img_tile * p.BN; e += 128) {
+					const int im_l = e / p.BN, c = e - im_l * p.BN, col = n0 + c;
+					float v = 0.f;
+					if (col < p.N) {
+						if (p.bias) v = __ldg(p.bias + col);
+						if (p.rowvec) {
+							const long long im = min((long long)(p.conv ? ti0 + im_l : 0), (long long)p.n_img - 1);
+							const long long o = im * p.rowvec_stride + col;
+							v += p.rowvec_dt == DT_F16 ? __half2float(((const __half*)p.rowvec)[o]) : ((const float*)p.rowvec)[o];
+						}
+					}
+					epi_vec[e] = v;
+				}
+			}
+			if (!p.residual && threadIdx.x == 0) tma_store_wait_read();    // with a residual the wait happened before its load
+			asm volatile("bar.sync 1, 128;" ::: "memory");
+			const float* my_vec = epi_vec + (n_img_tile > 1 ? ii * p.BN : 0);
+
+			mbar_wait(&acc_full[buf], (lt >> 1) & 1);
+			if (p.residual) mbar_wait(res_full, lt & 1);
+			tc_fence_after();
+			const uint32_t trow = tmem_base + buf * 256 + lane_off;
+			auto process = [&](const uint32_t* v, int c0) {
+				float f[16];
+				#pragma unroll
+				for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+				if (has_vec) {
+					#pragma unroll
+					for (int j = 0; j < 16; j += 4) { float4 t = *reinterpret_cast<const float4*>(my_vec + c0 + j); f[j] += t.x; f[j+1] += t.y; f[j+2] += t.z; f[j+3] += t.w; }
+				}
+				if (p.act != U_NONE) {
+					#pragma unroll
+					for (int j = 0; j < 16; ++j) f[j] = act_apply_tc(p.act, f[j]);
+				}
+				uint8_t* chunk = my_row + (c0 / STG_CHUNK_COLS) * STG_CHUNK_BYTES;
+				const uint32_t u0 = (uint32_t)((c0 % STG_CHUNK_COLS) >> 3);     // 0 or 2
+				uint4* s0 = reinterpret_cast<uint4*>(chunk + ((u0 ^ row_sw) << 4));
+				uint4* s1 = reinterpret_cast<uint4*>(chunk + (((u0 + 1) ^ row_sw) << 4));
+				if (p.residual) {
+					const uint4 ra = *s0, rb = *s1;
+					const __half2* ha = reinterpret_cast<const __half2*>(&ra); const __half2* hb = reinterpret_cast<const __half2*>(&rb);
+					#pragma unroll
+					for (int j = 0; j < 4; ++j) { float2 x = __half22float2(ha[j]), y = __half22float2(hb[j]);
+						f[2*j] += x.x; f[2*j+1] += x.y; f[8+2*j] += y.x; f[8+2*j+1] += y.y; }
+				}
+				uint4 a, b; __half2* pa = reinterpret_cast<__half2*>(&a); __half2* pb = reinterpret_cast<__half2*>(&b);
+				#pragma unroll
+				for (int j = 0; j < 4; ++j) { pa[j] = __floats2half2_rn(f[2*j], f[2*j+1]); pb[j] = __floats2half2_rn(f[8+2*j], f[8+2*j+1]); }
+				*s0 = a; *s1 = b;
+			};
+			// 16 accumulator columns at a time, the next tcgen05.ld in flight while the current ones are processed
+			uint32_t va[16], vb[16];
+			tmem_ld16(trow, va);
+			for (int c0 = 0; c0 < p.BN; c0 += 32) {
+				tmem_ld_wait();
+				if (c0 + 16 < p.BN) tmem_ld16(trow + (uint32_t)(c0 + 16), vb);
+				process(va, c0);
+				if (c0 + 16 < p.BN) {
+					tmem_ld_wait();
+					if (c0 + 32 < p.BN) tmem_ld16(trow + (uint32_t)(c0 + 32), va);
+					process(vb, c0 + 16);
+				}
+			}
+			// accumulator drained: hand the TMEM buffer back to the MMA warp (one arrival per warp)
+			tc_fence_before();
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&acc_empty[buf]);
+			fence_proxy_async();                           // staging writes -> visible to the TMA (async proxy)
+			asm volatile("bar.sync 1, 128;" ::: "memory");
+			if (threadIdx.x == 0) {
+				for (int c = 0; c < n_chunks; ++c) {
+					if (n0 + c * STG_CHUNK_COLS >= p.N) break;
+					if (p.conv) tma_store_4d(&tmC, stg + c * STG_CHUNK_BYTES, n0 + c * STG_CHUNK_COLS, tw0, th0, ti0);
+					else tma_store_2d(&tmC, stg + c * STG_CHUNK_BYTES, n0 + c * STG_CHUNK_COLS, m0);
+				}
+				tma_store_commit();
+				const int next = tile + gridDim.x;
+				if (p.residual && next < p.num_tiles) { tma_store_wait_read(); issue_res_load(next); }
+			}
+		}
+		if (threadIdx.x == 0) tma_store_wait_all();
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
 	const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -288,11 +522,11 @@ static PFN_encodeTiled get_encode()
 }
 
 static void encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-	const cuuint32_t* box)
+	const cuuint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B)
 {
 	cuuint32_t es[5] = {1, 1, 1, 1, 1};
 	CUresult r = get_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
-		box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+		box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
 		CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) {
 		B200_FATAL("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu %llu box %u %u %u %u base %p stride0 %llu", (int)r, rank,
@@ -338,6 +572,56 @@ static void finish_setup(GemmTC* g, const GemmEpilogue& ep, int64_t m_tiles, int
 	p.residual = ep.residual; p.residual_dt = ep.residual_dt; p.ldr = ep.ldr; p.act = ep.act;
 }
 
+// ---- persistent kernel setup
+static bool env_on(const char* n, bool dflt) { const char* e = getenv(n); return e && *e ? atoi(e) != 0 : dflt; }
+
+static bool persistent_eligible(const GemmParams& p, const GemmEpilogue& ep)
+{
+	if (!env_on("GGML_B200_GEMM_PERSISTENT", true)) return false;
+	if (p.c_dt != DT_F16 || (p.ldc % 8) || ((uintptr_t)p.C & 15)) return false;
+	if (ep.residual && (ep.residual_dt != DT_F16 || ep.ldr != p.ldc || ((uintptr_t)ep.residual & 15))) return false;
+	if (p.conv && ep.rowvec && p.bi > P_EPI_MAX_IMG) return false;
+	return true;
+}
+
+// N tile of the persistent kernel: minimise waves x per-tile cycles. Per tile the tensor pipe needs
+// num_kb * 4 MMAs of max(BN/2 [tcgen05 floor], 32 + BN/4 [A+B shared-memory reads at 128 B/clk]) cycles; the
+// operand tiles cost (128 + BN) * 128 B per k-block from L2 at ~58 B/clk per SM when all SMs pull (measured
+// ~17 TB/s chip-wide); the epilogue (~5 cycles per column) overlaps the next tile unless it is the longest.
+static int pick_bn_persistent(int64_t m_tiles, int64_t N, int num_kb, int sm_count)
+{
+	int best = 0; double best_cost = 1e30;
+	for (int bn = 256; bn >= 16; bn -= 16) {
+		if (bn - 16 >= N) continue;
+		const int64_t n_tiles = (N + bn - 1) / bn;
+		if (n_tiles > 1 && (bn % STG_CHUNK_COLS)) continue;       // staging chunks must not straddle tiles
+		const int64_t tiles = n_tiles * m_tiles, waves = (tiles + sm_count - 1) / sm_count;
+		const double mma = (double)num_kb * 4 * std::max(bn / 2.0, 32.0 + bn / 4.0), epi = 250.0 + 5.0 * bn;
+		const double l2 = (double)num_kb * (128.0 + bn) * 128.0 / 58.0;
+		const double cost = (double)waves * std::max(std::max(mma, l2), epi) + epi;
+		if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+	}
+	return best;
+}
+
+static void finish_setup_persistent(GemmTC* g, const GemmEpilogue& ep, int64_t m_tiles, int sm_count)
+{
+	GemmParams& p = g->p;
+	p.BN = pick_bn_persistent(m_tiles, p.N, p.num_kb, sm_count);
+	p.m_tiles = (int)m_tiles; p.n_tiles = (p.N + p.BN - 1) / p.BN; p.num_tiles = p.m_tiles * p.n_tiles;
+	const size_t stage = (size_t)BM * BK * 2 + (size_t)p.BN * BK * 2;
+	const size_t n_chunks = (p.BN + STG_CHUNK_COLS - 1) / STG_CHUNK_COLS;
+	const size_t fixed = 1024 + n_chunks * STG_CHUNK_BYTES + (size_t)P_EPI_MAX_IMG * 256 * 4 + (2 * MAX_STAGES + 5) * 8 + 64;
+	int stages = (int)std::min<size_t>(MAX_STAGES, (227 * 1024 - fixed) / stage);
+	p.stages = std::max(2, stages);
+	g->smem = fixed + p.stages * stage;
+	g->grid = dim3((unsigned)std::min<int64_t>(p.num_tiles, sm_count));
+	g->persistent = true;
+	p.bias = ep.bias; p.rowvec = ep.rowvec; p.rowvec_dt = ep.rowvec_dt; p.rowvec_stride = ep.rowvec_stride;
+	p.rows_per_image = ep.rows_per_image > 0 ? ep.rows_per_image : 1;
+	p.residual = ep.residual; p.residual_dt = ep.residual_dt; p.ldr = ep.ldr; p.act = ep.act;
+}
+
 GemmTC* gemm_tc_prepare(const __half* A, int64_t lda, const __half* B, int64_t ldb,
 	void* C, DT c_dt, int64_t ldc, int64_t M, int64_t N, int64_t K, const GemmEpilogue& ep, int sm_count)
 {
@@ -349,7 +633,13 @@ GemmTC* gemm_tc_prepare(const __half* A, int64_t lda, const __half* B, int64_t l
 	p.M = (int)M; p.N = (int)N; p.K = (int)K; p.num_kb = (int)((K + BK - 1) / BK);
 	p.C = C; p.c_dt = c_dt; p.ldc = ldc;
 	int64_t m_tiles = (M + BM - 1) / BM;
-	finish_setup(g, ep, m_tiles, sm_count);
+	if (persistent_eligible(p, ep)) {
+		finish_setup_persistent(g, ep, m_tiles, sm_count);
+		cuuint64_t dc[2] = { (cuuint64_t)N, (cuuint64_t)M }, sc[1] = { (cuuint64_t)ldc * 2 };
+		cuuint32_t bc[2] = { STG_CHUNK_COLS, BM };
+		encode_map(&g->tmC, C, 2, dc, sc, bc, CU_TENSOR_MAP_SWIZZLE_64B);
+		if (ep.residual) encode_map(&g->tmR, ep.residual, 2, dc, sc, bc, CU_TENSOR_MAP_SWIZZLE_64B);
+	} else finish_setup(g, ep, m_tiles, sm_count);
 	cuuint64_t da[2] = { (cuuint64_t)K, (cuuint64_t)M }, sa[1] = { (cuuint64_t)lda * 2 };
 	cuuint32_t ba[2] = { BK, BM };
 	encode_map(&g->tmA, A, 2, da, sa, ba);
@@ -388,7 +678,14 @@ GemmTC* conv3x3_tc_prepare(const __half* x, int64_t n_img, int64_t H, int64_t W,
 	p.tiles_h = (int)((H + p.bh - 1) / p.bh);
 	int64_t tiles_i = (n_img + p.bi - 1) / p.bi;
 	int64_t m_tiles = (int64_t)p.tiles_w * p.tiles_h * tiles_i;
-	finish_setup(g, ep, m_tiles, sm_count);
+	if (persistent_eligible(p, ep)) {
+		finish_setup_persistent(g, ep, m_tiles, sm_count);
+		cuuint64_t dc[4] = { (cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img };
+		cuuint64_t sc[3] = { (cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2 };
+		cuuint32_t bc[4] = { STG_CHUNK_COLS, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bi };
+		encode_map(&g->tmC, C, 4, dc, sc, bc, CU_TENSOR_MAP_SWIZZLE_64B);
+		if (ep.residual) encode_map(&g->tmR, ep.residual, 4, dc, sc, bc, CU_TENSOR_MAP_SWIZZLE_64B);
+	} else finish_setup(g, ep, m_tiles, sm_count);
 	cuuint64_t da[4] = { (cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img };
 	cuuint64_t sa[3] = { (cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2 };
 	cuuint32_t ba[4] = { BK, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bi };
@@ -404,9 +701,11 @@ void gemm_tc_launch(cudaStream_t s, GemmTC* g)
 	static bool attr_set = false;
 	if (!attr_set) {
 		CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		attr_set = true;
 	}
-	gemm_tc_kernel<<<g->grid, 192, g->smem, s>>>(g->tmA, g->tmB, g->p);
+	if (g->persistent) gemm_tc_persistent_kernel<<<g->grid, P_THREADS, g->smem, s>>>(g->tmA, g->tmB, g->tmC, g->tmR, g->p);
+	else gemm_tc_kernel<<<g->grid, 192, g->smem, s>>>(g->tmA, g->tmB, g->p);
 	g_stats.kernel_launches++;
 }
 

@@ -81,8 +81,62 @@ __global__ void copy_kernel(V4 dst, V4 src, Iter4 it)
 		else stv(dst, offs(dst, i), ldv(src, offs(src, i)));
 	}
 }
+// Fast path (concat halves, pad interiors, nearest upscale, layout-preserving copies): both views have the same
+// unit-stride dim whose extent, the other strides and both base pointers are multiples of 16 bytes. One 16-byte
+// vector per thread step; src index = dst index / f (f = 1 for plain copies, the scale factors for upscale).
+struct VecCopy {
+	const uint4* src; uint4* dst;
+	int n[4];                  // extents in iteration order, n[0] = vectors along the contiguous dim
+	long long ds[4], ss[4];    // strides in vectors
+	int f[4];                  // src index divisor per iteration dim
+	long long total;
+};
+__global__ void vec_copy_kernel(VecCopy c)
+{
+	for (long long lin = blockIdx.x * (long long)blockDim.x + threadIdx.x; lin < c.total; lin += (long long)gridDim.x * blockDim.x) {
+		long long r = lin;
+		const int i0 = (int)(r % c.n[0]); r /= c.n[0];
+		const int i1 = (int)(r % c.n[1]); r /= c.n[1];
+		const int i2 = (int)(r % c.n[2]); const int i3 = (int)(r / c.n[2]);
+		c.dst[i0 * c.ds[0] + i1 * c.ds[1] + i2 * c.ds[2] + i3 * c.ds[3]] =
+			__ldg(c.src + i0 * c.ss[0] + (i1 / c.f[1]) * c.ss[1] + (i2 / c.f[2]) * c.ss[2] + (i3 / c.f[3]) * c.ss[3]);
+	}
+}
+static bool try_vec_copy(cudaStream_t s, const View& dst, const View& src)
+{
+	if (dst.dt != src.dt || dst.dt == DT_I32) return false;
+	const int es = (int)dt_size(dst.dt), vl = 16 / es;
+	int d0 = -1;
+	for (int i = 0; i < 4; ++i) if (dst.ne[i] > 1 && dst.st[i] == 1 && src.st[i] == 1 && dst.ne[i] == src.ne[i]) { d0 = i; break; }
+	if (d0 < 0 || dst.ne[d0] % vl || ((uintptr_t)dst.ptr & 15) || ((uintptr_t)src.ptr & 15)) return false;
+	int f[4];
+	for (int i = 0; i < 4; ++i) {
+		if (src.ne[i] <= 0 || dst.ne[i] % src.ne[i]) return false;
+		f[i] = (int)(dst.ne[i] / src.ne[i]);
+		if (i != d0 && ((dst.ne[i] > 1 && dst.st[i] % vl) || (src.ne[i] > 1 && src.st[i] % vl))) return false;
+		if (dst.ne[i] > 0x7fffffff) return false;
+	}
+	// iteration order: contiguous dim first, then the others by increasing dst stride
+	int ord[4], k = 0; ord[k++] = d0;
+	for (int i = 0; i < 4; ++i) if (i != d0) ord[k++] = i;
+	std::stable_sort(ord + 1, ord + 4, [&](int a, int b) {
+		long long sa = dst.ne[a] == 1 ? (1LL << 60) : dst.st[a], sb = dst.ne[b] == 1 ? (1LL << 60) : dst.st[b]; return sa < sb; });
+	VecCopy c; c.src = (const uint4*)src.ptr; c.dst = (uint4*)dst.ptr; c.total = 1;
+	for (int j = 0; j < 4; ++j) {
+		const int i = ord[j];
+		c.n[j] = (int)(j == 0 ? dst.ne[i] / vl : dst.ne[i]);
+		c.ds[j] = j == 0 ? 1 : dst.st[i] / vl; c.ss[j] = j == 0 ? 1 : src.st[i] / vl; c.f[j] = j == 0 ? 1 : f[i];
+		c.total *= c.n[j];
+	}
+	if (!c.total) return true;
+	vec_copy_kernel<<<grid_for(c.total, 256, 2), 256, 0, s>>>(c);
+	g_stats.kernel_launches++;
+	return true;
+}
+
 void k_copy(cudaStream_t s, const View& dst, const View& src)
 {
+	if (try_vec_copy(s, dst, src)) return;
 	Iter4 it = iter_for(dst);
 	if (!it.total) return;
 	copy_kernel<<<grid_for(it.total, 256), 256, 0, s>>>(v4(dst), v4(src), it);
@@ -138,6 +192,7 @@ __global__ void upscale_kernel(V4 dst, V4 src, Iter4 it, int f0, int f1)
 }
 void k_upscale(cudaStream_t s, const View& dst, const View& src)
 {
+	if (dst.ne[2] == src.ne[2] && dst.ne[3] == src.ne[3] && try_vec_copy(s, dst, src)) return;
 	Iter4 it = iter_for(dst);
 	upscale_kernel<<<grid_for(it.total, 256), 256, 0, s>>>(v4(dst), v4(src), it,
 		(int)(dst.ne[0] / src.ne[0]), (int)(dst.ne[1] / src.ne[1]));
@@ -371,6 +426,114 @@ __global__ void gn_apply_kernel(const TI* __restrict__ x, TO* __restrict__ y, lo
 	}
 }
 
+// ---- fast path (f16 in, f16 out): a thread owns ONE 8-channel chunk for its whole life, so mean/rstd/gamma/beta
+// fold into 8 scale + 8 shift registers once and the pixel loop is load -> 8 FMA (-> SiLU) -> store, four pixels
+// in flight per thread. Same (chunk, plane) thread mapping as the statistics pass: a warp touches contiguous memory.
+__device__ __forceinline__ void h8_to_f(const uint4& raw, float* v)
+{
+	const __half2* h = reinterpret_cast<const __half2*>(&raw);
+	#pragma unroll
+	for (int j = 0; j < 4; ++j) { float2 f = __half22float2(h[j]); v[2*j] = f.x; v[2*j+1] = f.y; }
+}
+__device__ __forceinline__ uint4 f_to_h8(const float* v)
+{
+	uint4 raw; __half2* h = reinterpret_cast<__half2*>(&raw);
+	#pragma unroll
+	for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[2*j], v[2*j+1]);
+	return raw;
+}
+
+__global__ void gn_stats_fast_kernel(const __half* __restrict__ x, long long HW, int C, int cpg, int groups,
+	long long img_stride, long long pix_stride, double* __restrict__ stats, int pix_per_block, int slab_chunks, int nslabs)
+{
+	extern __shared__ float sm[];  // [groups][2]
+	const int n = blockIdx.y;
+	const int tile = blockIdx.x / nslabs, slab = blockIdx.x - tile * nslabs;
+	for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sm[i] = 0.f;
+	__syncthreads();
+	const int chunks = C / 8;
+	const int ch = slab * slab_chunks + (int)(threadIdx.x % slab_chunks);
+	const int plane = threadIdx.x / slab_chunks, planes = blockDim.x / slab_chunks;
+	const long long p0 = (long long)tile * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+	if (ch < chunks) {
+		float su[8], sq[8];
+		#pragma unroll
+		for (int j = 0; j < 8; ++j) { su[j] = 0.f; sq[j] = 0.f; }
+		const __half* base = x + n * img_stride + ch * 8;
+		long long p = p0 + plane;
+		for (; p + 3 * planes < p1; p += 4 * planes) {
+			uint4 r[4];
+			#pragma unroll
+			for (int u = 0; u < 4; ++u) r[u] = *reinterpret_cast<const uint4*>(base + (p + u * planes) * pix_stride);
+			#pragma unroll
+			for (int u = 0; u < 4; ++u) { float v[8]; h8_to_f(r[u], v);
+				#pragma unroll
+				for (int j = 0; j < 8; ++j) { su[j] += v[j]; sq[j] = fmaf(v[j], v[j], sq[j]); } }
+		}
+		for (; p < p1; p += planes) {
+			float v[8]; h8_to_f(*reinterpret_cast<const uint4*>(base + p * pix_stride), v);
+			#pragma unroll
+			for (int j = 0; j < 8; ++j) { su[j] += v[j]; sq[j] = fmaf(v[j], v[j], sq[j]); }
+		}
+		int g = (ch * 8) / cpg;
+		float a = 0.f, b = 0.f;
+		#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			int gj = (ch * 8 + j) / cpg;
+			if (gj != g) { atomicAdd(&sm[g * 2], a); atomicAdd(&sm[g * 2 + 1], b); a = 0.f; b = 0.f; g = gj; }
+			a += su[j]; b += sq[j];
+		}
+		atomicAdd(&sm[g * 2], a); atomicAdd(&sm[g * 2 + 1], b);
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < groups * 2; i += blockDim.x)
+		if (sm[i] != 0.f) atomicAdd(&stats[(long long)n * groups * 2 + i], (double)sm[i]);
+}
+
+template <bool SILU>
+__global__ void gn_apply_fast_kernel(const __half* __restrict__ x, __half* __restrict__ y, long long HW, int C, int cpg, int groups,
+	long long img_stride, long long pix_stride, long long oimg_stride, long long opix_stride,
+	const float* __restrict__ gamma, const float* __restrict__ beta, const double* __restrict__ stats,
+	float eps, int pix_per_block, int slab_chunks, int nslabs)
+{
+	const int n = blockIdx.y;
+	const int tile = blockIdx.x / nslabs, slab = blockIdx.x - tile * nslabs;
+	const int chunks = C / 8;
+	const int ch = slab * slab_chunks + (int)(threadIdx.x % slab_chunks);
+	const int plane = threadIdx.x / slab_chunks, planes = blockDim.x / slab_chunks;
+	if (ch >= chunks) return;
+	const double cnt = (double)HW * cpg;
+	float sc[8], sh[8];
+	#pragma unroll
+	for (int j = 0; j < 8; ++j) {
+		const int c = ch * 8 + j, g = c / cpg;
+		const double su = stats[((long long)n * groups + g) * 2], sq = stats[((long long)n * groups + g) * 2 + 1];
+		const double mean = su / cnt; double var = sq / cnt - mean * mean; if (var < 0) var = 0;
+		const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+		const float ga = gamma ? gamma[c] : 1.f, be = (gamma && beta) ? beta[c] : 0.f;
+		sc[j] = rstd * ga; sh[j] = be - (float)mean * rstd * ga;
+	}
+	const long long p0 = (long long)tile * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+	const __half* base = x + n * img_stride + ch * 8;
+	__half* obase = y + n * oimg_stride + ch * 8;
+	auto apply = [&](const uint4& raw) {
+		float v[8]; h8_to_f(raw, v);
+		#pragma unroll
+		for (int j = 0; j < 8; ++j) { float t = fmaf(v[j], sc[j], sh[j]); if (SILU) t = __fdividef(t, 1.0f + __expf(-t)); v[j] = t; }
+		return f_to_h8(v);
+	};
+	long long p = p0 + plane;
+	for (; p + 3 * planes < p1; p += 4 * planes) {
+		uint4 r[4];
+		#pragma unroll
+		for (int u = 0; u < 4; ++u) r[u] = *reinterpret_cast<const uint4*>(base + (p + u * planes) * pix_stride);
+		#pragma unroll
+		for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(obase + (p + u * planes) * opix_stride) = apply(r[u]);
+	}
+	for (; p < p1; p += planes)
+		*reinterpret_cast<uint4*>(obase + p * opix_stride) = apply(*reinterpret_cast<const uint4*>(base + p * pix_stride));
+}
+
 void k_groupnorm(cudaStream_t s, const View& dst, const View& src, const float* gamma, const float* beta,
 	int groups, float eps, bool silu, double* stats)
 {
@@ -378,6 +541,27 @@ void k_groupnorm(cudaStream_t s, const View& dst, const View& src, const float* 
 	int cpg = (C + groups - 1) / groups;
 	if (src.st[2] != 1 || dst.st[2] != 1 || C % 8 || src.st[1] != W * src.st[0] || dst.st[1] != W * dst.st[0])
 		B200_FATAL("k_groupnorm: unsupported layout (C=%d)", C);
+	if (src.dt == DT_F16 && dst.dt == DT_F16 && !((uintptr_t)src.ptr & 15) && !((uintptr_t)dst.ptr & 15) &&
+		src.st[0] % 8 == 0 && dst.st[0] % 8 == 0 && src.st[3] % 8 == 0 && dst.st[3] % 8 == 0) {
+		const int chunks = C / 8;
+		const int nslabs = (chunks + 255) / 256, slab_chunks = (chunks + nslabs - 1) / nslabs;
+		const int planes = std::max(1, 256 / slab_chunks), threads = slab_chunks * planes;
+		// pixels per block: 16 per thread, fewer for small tensors so that the grid still covers the chip twice
+		int ppt = 16;
+		while (ppt > 2 && ((HW + (long long)planes * ppt - 1) / ((long long)planes * ppt)) * N * nslabs < 148LL * 4) ppt /= 2;
+		const int pix_per_block = planes * ppt;
+		dim3 grid((unsigned)(((HW + pix_per_block - 1) / pix_per_block) * nslabs), (unsigned)N);
+		const size_t smem = groups * 2 * sizeof(float);
+		gn_stats_fast_kernel<<<grid, threads, smem, s>>>((const __half*)src.ptr, HW, C, cpg, groups, src.st[3], src.st[0], stats, pix_per_block, slab_chunks, nslabs);
+		if (silu)
+			gn_apply_fast_kernel<true><<<grid, threads, 0, s>>>((const __half*)src.ptr, (__half*)dst.ptr, HW, C, cpg, groups, src.st[3], src.st[0],
+				dst.st[3], dst.st[0], gamma, beta, stats, eps, pix_per_block, slab_chunks, nslabs);
+		else
+			gn_apply_fast_kernel<false><<<grid, threads, 0, s>>>((const __half*)src.ptr, (__half*)dst.ptr, HW, C, cpg, groups, src.st[3], src.st[0],
+				dst.st[3], dst.st[0], gamma, beta, stats, eps, pix_per_block, slab_chunks, nslabs);
+		g_stats.kernel_launches += 2;
+		return;
+	}
 	int threads = 256;
 	int chunks = C / 8;
 	int slab_chunks = std::min(chunks, 64), nslabs = (chunks + slab_chunks - 1) / slab_chunks;
@@ -472,6 +656,76 @@ __global__ void layernorm_kernel(const TI* __restrict__ x, TO* __restrict__ y, l
 	}
 }
 
+// ---- fast path (f16 -> f16): a warp walks rows with a grid stride; gamma / beta live in registers for the whole
+// kernel (vector loads, once), and the next row is already in flight while the current one is reduced and stored.
+template <int NCH>
+__global__ void layernorm_fast_kernel(const __half* __restrict__ x, __half* __restrict__ y, long long rows, int C,
+	long long ld_in, long long ld_out, const float* __restrict__ gamma, const float* __restrict__ beta, float eps)
+{
+	const int lane = threadIdx.x & 31, chunks = C >> 3;
+	const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+	long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+	float ga[NCH][8], be[NCH][8];
+	#pragma unroll
+	for (int i = 0; i < NCH; ++i) {
+		const int ch = lane + i * 32;
+		#pragma unroll
+		for (int j = 0; j < 8; ++j) { ga[i][j] = 1.f; be[i][j] = 0.f; }
+		if (ch < chunks && gamma) {
+			const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8 + 4));
+			ga[i][0] = g0.x; ga[i][1] = g0.y; ga[i][2] = g0.z; ga[i][3] = g0.w; ga[i][4] = g1.x; ga[i][5] = g1.y; ga[i][6] = g1.z; ga[i][7] = g1.w;
+			if (beta) {
+				const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + ch * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + ch * 8 + 4));
+				be[i][0] = b0.x; be[i][1] = b0.y; be[i][2] = b0.z; be[i][3] = b0.w; be[i][4] = b1.x; be[i][5] = b1.y; be[i][6] = b1.z; be[i][7] = b1.w;
+			}
+		}
+	}
+	uint4 cur[NCH], nxt[NCH];
+	auto load = [&](long long r, uint4* dst) {
+		#pragma unroll
+		for (int i = 0; i < NCH; ++i) { const int ch = lane + i * 32; if (ch < chunks) dst[i] = *reinterpret_cast<const uint4*>(x + r * ld_in + ch * 8); }
+	};
+	if (row < rows) load(row, cur);
+	const float inv_c = 1.0f / C;
+	for (; row < rows; row += wstride) {
+		const long long nrow = row + wstride;
+		if (nrow < rows) load(nrow, nxt);
+		float v[NCH][8];
+		float sum = 0.f;
+		#pragma unroll
+		for (int i = 0; i < NCH; ++i) {
+			if (lane + i * 32 < chunks) { h8_to_f(cur[i], v[i]);
+				#pragma unroll
+				for (int j = 0; j < 8; ++j) sum += v[i][j]; }
+		}
+		#pragma unroll
+		for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(~0u, sum, o);
+		const float mean = sum * inv_c;
+		float sq = 0.f;
+		#pragma unroll
+		for (int i = 0; i < NCH; ++i)
+			if (lane + i * 32 < chunks) {
+				#pragma unroll
+				for (int j = 0; j < 8; ++j) { v[i][j] -= mean; sq = fmaf(v[i][j], v[i][j], sq); }
+			}
+		#pragma unroll
+		for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(~0u, sq, o);
+		const float rstd = rsqrtf(sq * inv_c + eps);
+		#pragma unroll
+		for (int i = 0; i < NCH; ++i) {
+			const int ch = lane + i * 32;
+			if (ch < chunks) {
+				float t[8];
+				#pragma unroll
+				for (int j = 0; j < 8; ++j) t[j] = fmaf(v[i][j] * rstd, ga[i][j], be[i][j]);
+				*reinterpret_cast<uint4*>(y + row * ld_out + ch * 8) = f_to_h8(t);
+			}
+		}
+		#pragma unroll
+		for (int i = 0; i < NCH; ++i) cur[i] = nxt[i];
+	}
+}
+
 // scalar fallback for row lengths that are not multiples of 8 (or unaligned rows)
 template <typename TI, typename TO>
 __global__ void layernorm_scalar_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long rows, int C,
@@ -505,6 +759,16 @@ static void layernorm_launch(cudaStream_t s, const void* x, void* y, long long r
 	unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
 	bool vec = C % 8 == 0 && ldi % 8 == 0 && ldo % 8 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0 && C <= 2048;
 	if (!vec) { layernorm_scalar_kernel<TI, TO><<<grid, wpb * 32, 0, s>>>((const TI*)x, (TO*)y, rows, C, ldi, ldo, g, b, eps); return; }
+	if (sizeof(TI) == 2 && sizeof(TO) == 2 && C <= 256 * 5 && (!g || !((uintptr_t)g & 15)) && (!b || !((uintptr_t)b & 15))) {
+		// grid-stride fast path: 4 rows per warp at least, at most 16 blocks of 8 warps per SM
+		unsigned fg = (unsigned)std::min<long long>((rows + wpb * 4 - 1) / (wpb * 4), 148LL * 16);
+		fg = std::max(fg, 1u);
+		if (C <= 256) layernorm_fast_kernel<1><<<fg, wpb * 32, 0, s>>>((const __half*)x, (__half*)y, rows, C, ldi, ldo, g, b, eps);
+		else if (C <= 512) layernorm_fast_kernel<2><<<fg, wpb * 32, 0, s>>>((const __half*)x, (__half*)y, rows, C, ldi, ldo, g, b, eps);
+		else if (C <= 768) layernorm_fast_kernel<3><<<fg, wpb * 32, 0, s>>>((const __half*)x, (__half*)y, rows, C, ldi, ldo, g, b, eps);
+		else layernorm_fast_kernel<5><<<fg, wpb * 32, 0, s>>>((const __half*)x, (__half*)y, rows, C, ldi, ldo, g, b, eps);
+		return;
+	}
 	if (C <= 256 * 2) layernorm_kernel<TI, TO, 2><<<grid, wpb * 32, 0, s>>>((const TI*)x, (TO*)y, rows, C, ldi, ldo, g, b, eps);
 	else if (C <= 256 * 5) layernorm_kernel<TI, TO, 5><<<grid, wpb * 32, 0, s>>>((const TI*)x, (TO*)y, rows, C, ldi, ldo, g, b, eps);
 	else layernorm_kernel<TI, TO, 8><<<grid, wpb * 32, 0, s>>>((const TI*)x, (TO*)y, rows, C, ldi, ldo, g, b, eps);

@@ -25,5 +25,15 @@ for spec in sys.argv[1:]:
     n = 20
     for _ in range(n): G.compute()
     ms = lib.ggml_b200_timer_stop() / n
-    print("%-28s %9.1f us  %8.1f TFLOP/s (whole graph incl. input conversion)" % (spec, ms * 1e3, flops / ms / 1e9))
+    # kernel-only time: profiled eager pass (CUDA events around each step), tcgen05 GEMM + conv kinds
+    lib.ggml_b200_profile_enable(1)
+    for _ in range(5): G.compute()
+    kms = 0.0
+    for kind in (14, 15):
+        a, b_, c_, l = C.c_double(), C.c_double(), C.c_double(), C.c_uint64()
+        lib.ggml_b200_profile_get(kind, C.byref(a), C.byref(b_), C.byref(c_), C.byref(l))
+        kms += a.value
+    kms /= 5
+    lib.ggml_b200_profile_enable(0)
+    print("%-28s kernel %8.1f us %7.1f TFLOP/s | graph incl. layout conversion %9.1f us" % (spec, kms * 1e3, flops / kms / 1e9 if kms else 0, ms * 1e3))
     G.free()
