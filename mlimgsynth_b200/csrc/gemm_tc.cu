@@ -38,6 +38,11 @@ struct GemmParams {
 	const void* residual; int residual_dt; long long ldr;
 	int act;
 	int m_tiles, n_tiles, num_tiles;   // persistent kernel: static tile schedule
+	// thread-block cluster of cm x cn CTAs working on cm m-tiles x cn n-tiles: every A tile is loaded once per
+	// cluster row (each of its cn CTAs fetches 1/cn of the rows and TMA-multicasts them), every B tile once per column
+	int cm, cn, a_rows, b_rows, a_split_dim, a_split_ext, m_ctiles, n_ctiles;
+	int n_stg;                         // staging tiles (2: the TMA store of tile i drains while tile i+1 is written)
+	long long* trace;                  // debug timeline of CTA 0's epilogue (GGML_B200_GEMM_TRACE), null in production
 };
 
 struct GemmTC {
@@ -275,14 +280,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // ------------------------------------------------------------------ the persistent kernel (v2)
 // One CTA per SM walks a static list of output tiles (n fastest, so CTAs of a wave share activation rows in L2):
-//   warps 0..3  epilogue (TMEM lane quarter = warp id): accumulator -> registers (tcgen05.ld) -> + bias / per-image
+//   warps 0..7  epilogue (TMEM lane quarter = warp % 4, column half = warp / 4): accumulator -> registers (tcgen05.ld) -> + bias / per-image
 //               vector (staged in shared memory), activation, + residual (TMA-loaded into the staging tile) ->
 //               f16 -> 64B-swizzled staging tile -> TMA store. Global traffic of the epilogue is bulk-async only.
-//   warp 4      TMA producer, warp 5 MMA issuer: both run warp-uniform control flow with one elected lane issuing,
+//   warp 8      TMA producer, warp 9 MMA issuer: both run warp-uniform control flow with one elected lane issuing,
 //               so descriptors live in uniform registers (no R2UR per instruction); highest warp ids = issue priority.
 // The accumulator is double-buffered in tensor memory (2 x 256 columns): the epilogue of tile i overlaps the main
 // loop of tile i+1, and barrier setup / TMEM allocation / descriptor prefetch happen once per SM, not per tile.
-constexpr int P_THREADS = 192;
+constexpr int P_THREADS = 320;                           // 8 epilogue warps + TMA producer + MMA issuer
 constexpr int P_EPI_MAX_IMG = 8;
 constexpr int STG_CHUNK_COLS = 32;                        // staging chunk: [128 rows][32 f16] = 8 KB, SWIZZLE_64B
 constexpr int STG_CHUNK_BYTES = BM * STG_CHUNK_COLS * 2;
@@ -299,8 +304,32 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* 
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, uint16_t mask)
+{
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+		:: "r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_mc(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3, uint16_t mask)
+{
+	asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+		:: "r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask) : "memory");
+}
+// arrive on the same barrier offset in every CTA of `mask` once all previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask)
+{
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+		:: "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all()
+{ asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_count_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+
+template <int ACT, bool HAS_RES>     // ACT: 0 none, 1 SiLU, 2 run-time p.act; HAS_RES: f16 residual tile added in the epilogue
 __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
 	const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmParams p)
@@ -310,7 +339,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 	const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)p.BN * BK * 2, stage_bytes = a_bytes + b_bytes;
 	const int n_chunks = (p.BN + STG_CHUNK_COLS - 1) / STG_CHUNK_COLS;
 	uint8_t* stg = smem + (size_t)p.stages * stage_bytes;                       // staging tile (1024-aligned)
-	float* epi_vec = (float*)(stg + (size_t)n_chunks * STG_CHUNK_BYTES);        // [P_EPI_MAX_IMG][BN]
+	float* epi_vec = (float*)(stg + (size_t)p.n_stg * n_chunks * STG_CHUNK_BYTES);   // [P_EPI_MAX_IMG][BN]
 	uint64_t* full_bar  = (uint64_t*)(epi_vec + P_EPI_MAX_IMG * 256);
 	uint64_t* empty_bar = full_bar + MAX_STAGES;
 	uint64_t* acc_full  = empty_bar + MAX_STAGES;      // [2]
@@ -319,23 +348,34 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 	uint32_t* tmem_slot = (uint32_t*)(res_full + 1);
 
 	const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
+	const int csize = p.cm * p.cn;
+	const int crank = csize > 1 ? (int)cluster_ctarank() : 0, rn = crank % p.cn, rm = crank / p.cn;
+	const int cluster = csize > 1 ? (int)cluster_id_x() : (int)blockIdx.x, nclusters = csize > 1 ? (int)cluster_count_x() : (int)gridDim.x;
+	const int num_ctiles = p.m_ctiles * p.n_ctiles;
+	// CTAs sharing my A tile (same cluster row) / my B tile (same cluster column)
+	uint16_t row_mask = 0, col_mask = 0;
+	for (int j = 0; j < p.cn; ++j) row_mask |= (uint16_t)(1u << (rm * p.cn + j));
+	for (int i = 0; i < p.cm; ++i) col_mask |= (uint16_t)(1u << (i * p.cn + rn));
 	if (threadIdx.x == 0) {
 		tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmC);
 		if (p.residual) tma_prefetch_desc(&tmR);
-		for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-		for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+		// a ring slot is free once every CTA that multicasts into it has seen ALL its readers release it
+		for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], p.cm + p.cn - 1); }
+		for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
 		mbar_init(res_full, 1);
 		fence_barrier_init();
 	}
-	if (warp == 5) tmem_alloc(tmem_slot, 512);
+	if (warp == 9) tmem_alloc(tmem_slot, 512);
 	tc_fence_before();
 	__syncthreads();
+	if (csize > 1) cluster_sync_all();                 // peers' barriers exist before anything is multicast to them
 	tc_fence_after();
 	const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
-	// tile id -> coordinates (n fastest)
+	// cluster tile id -> this CTA's tile coordinates (n fastest). Tiles past the edge (odd tile counts) are processed
+	// like any other: their loads are zero-filled and their stores clipped by the TMA unit.
 	auto tile_coords = [&](int tile, int& n0, int& m0, int& tw0, int& th0, int& ti0) {
-		const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+		const int nt = (tile % p.n_ctiles) * p.cn + rn, mt = (tile / p.n_ctiles) * p.cm + rm;
 		n0 = nt * p.BN; m0 = mt * BM; tw0 = th0 = ti0 = 0;
 		if (p.conv) {
 			const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, ti = mt / (p.tiles_w * p.tiles_h);
@@ -343,38 +383,45 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 		}
 	};
 
-	if (warp == 4) {
+	if (warp == 8) {
 		// ===== TMA producer =====
 		const int cpt = p.conv ? p.Cin / BK : 1;          // channel chunks per filter tap
 		int s = 0; uint32_t ph = 0;                        // ring slot and its phase, carried across tiles (no division in the loop)
-		for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+		for (int tile = cluster; tile < num_ctiles; tile += nclusters) {
 			int n0, m0, tw0, th0, ti0; tile_coords(tile, n0, m0, tw0, th0, ti0);
 			int tap = 0, cc = 0;
 			for (int kb = 0; kb < p.num_kb; ++kb) {
 				mbar_wait(&empty_bar[s], ph ^ 1);
 				if (elect_one()) {
 					uint8_t* sa = smem + (size_t)s * stage_bytes;
-					mbar_expect_tx(&full_bar[s], stage_bytes);
+					mbar_expect_tx(&full_bar[s], stage_bytes);      // my slice + the slices the peers multicast to me
+					uint8_t* sa_slice = sa + rn * p.a_rows * 128;
+					uint8_t* sb_slice = sa + a_bytes + rm * p.b_rows * 128;
 					if (p.conv) {
 						const int kh = (tap * 11) >> 5, kw = tap - kh * 3;      // tap / 3 for tap < 9
-						tma_load_4d(sa, &tmA, &full_bar[s], cc * BK, tw0 + kw - 1, th0 + kh - 1, ti0);
+						int cw = tw0 + kw - 1, chh = th0 + kh - 1, ci = ti0;
+						if (p.a_split_dim == 3) ci += rn * p.a_split_ext; else if (p.a_split_dim == 2) chh += rn * p.a_split_ext; else cw += rn * p.a_split_ext;
+						if (p.cn > 1) tma_load_4d_mc(sa_slice, &tmA, &full_bar[s], cc * BK, cw, chh, ci, row_mask);
+						else tma_load_4d(sa_slice, &tmA, &full_bar[s], cc * BK, cw, chh, ci);
 					} else {
-						tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m0);
+						if (p.cn > 1) tma_load_2d_mc(sa_slice, &tmA, &full_bar[s], kb * BK, m0 + rn * p.a_rows, row_mask);
+						else tma_load_2d(sa_slice, &tmA, &full_bar[s], kb * BK, m0);
 					}
-					tma_load_2d(sa + a_bytes, &tmB, &full_bar[s], kb * BK, n0);
+					if (p.cm > 1) tma_load_2d_mc(sb_slice, &tmB, &full_bar[s], kb * BK, n0 + rm * p.b_rows, col_mask);
+					else tma_load_2d(sb_slice, &tmB, &full_bar[s], kb * BK, n0);
 				}
 				__syncwarp();
 				if (++cc == cpt) { cc = 0; ++tap; }
 				if (++s == p.stages) { s = 0; ph ^= 1; }
 			}
 		}
-	} else if (warp == 5) {
+	} else if (warp == 9) {
 		// ===== MMA issuer =====
 		const uint32_t idesc = make_idesc(p.BN);
 		const uint64_t adesc0 = make_smem_desc(smem_u32(smem)), bdesc0 = make_smem_desc(smem_u32(smem) + a_bytes);
 		const uint32_t stage16 = stage_bytes >> 4;
 		int s = 0; uint32_t ph = 0, lt = 0;                // ring slot / phase, local tile counter
-		for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+		for (int tile = cluster; tile < num_ctiles; tile += nclusters, ++lt) {
 			const uint32_t buf = lt & 1;
 			mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);       // epilogue drained this accumulator
 			tc_fence_after();
@@ -387,7 +434,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 					#pragma unroll
 					for (int k = 0; k < BK / 16; ++k)
 						umma_f16(td, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
-					umma_commit(&empty_bar[s]);
+					if (csize > 1) umma_commit_mc(&empty_bar[s], (uint16_t)(row_mask | col_mask));
+					else umma_commit(&empty_bar[s]);
 					if (kb == p.num_kb - 1) umma_commit(&acc_full[buf]);
 				}
 				__syncwarp();
@@ -395,50 +443,76 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 			}
 		}
 	} else {
-		// ===== epilogue warps 0..3 =====
-		const int r = warp * 32 + lane;                    // row of the tile = TMEM lane
-		const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+		// ===== epilogue warps 0..7: TMEM lane quarter = warp % 4, column half = warp / 4 =====
+		const int quarter = warp & 3, grp = warp >> 2;
+		const int r = quarter * 32 + lane;                 // row of the tile = TMEM lane
+		const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
 		const uint32_t row_sw = (uint32_t)((r >> 1) & 3);  // SWIZZLE_64B: 16-byte unit index ^= address bits [7,8]
-		uint8_t* my_row = stg + r * 64;
+		const uint32_t stg_bytes = (uint32_t)n_chunks * STG_CHUNK_BYTES;
+		const uint32_t my_row0 = smem_u32(stg) + r * 64;   // shared-space address of this row in chunk 0 of staging tile 0
 		const bool has_vec = p.bias || p.rowvec;
 		const int n_img_tile = (p.conv && p.rowvec) ? p.bi : 1;
 		const int ii = p.conv ? r / (p.bw * p.bh) : 0;     // image of this row inside the tile
-		auto issue_res_load = [&](int tile) {              // one thread: residual tile -> staging
-			int n0, m0, tw0, th0, ti0; tile_coords(tile, n0, m0, tw0, th0, ti0);
-			mbar_expect_tx(res_full, (uint32_t)n_chunks * STG_CHUNK_BYTES);
-			for (int c = 0; c < n_chunks; ++c) {
-				if (p.conv) tma_load_4d(stg + c * STG_CHUNK_BYTES, &tmR, res_full, n0 + c * STG_CHUNK_COLS, tw0, th0, ti0);
-				else tma_load_2d(stg + c * STG_CHUNK_BYTES, &tmR, res_full, n0 + c * STG_CHUNK_COLS, m0);
-			}
-		};
-		if (p.residual && threadIdx.x == 0 && (int)blockIdx.x < p.num_tiles) issue_res_load(blockIdx.x);
-		uint32_t lt = 0;
-		for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
-			int n0, m0, tw0, th0, ti0; tile_coords(tile, n0, m0, tw0, th0, ti0);
-			const uint32_t buf = lt & 1;
-			// stage bias (+ per-image vector) of this tile's columns; the previous store must have left the staging tile
-			if (has_vec) {
-				for (int e = threadIdx.x; e < n_img_tile * p.BN; e += 128) {
-					const int im_l = e / p.BN, c = e - im_l * p.BN, col = n0 + c;
-					float v = 0.f;
-					if (col < p.N) {
-						if (p.bias) v = __ldg(p.bias + col);
-						if (p.rowvec) {
-							const long long im = min((long long)(p.conv ? ti0 + im_l : 0), (long long)p.n_img - 1);
-							const long long o = im * p.rowvec_stride + col;
-							v += p.rowvec_dt == DT_F16 ? __half2float(((const __half*)p.rowvec)[o]) : ((const float*)p.rowvec)[o];
-						}
-					}
-					epi_vec[e] = v;
+		const int half_chunks = (n_chunks + 1) >> 1;
+		const int c_lo = grp * half_chunks * STG_CHUNK_COLS, c_hi = min(p.BN, (grp + 1) * half_chunks * STG_CHUNK_COLS);
+		const int et = threadIdx.x;                        // 0..255 among the epilogue threads
+		const bool chunk_owner = lane == 0 && warp < n_chunks;    // lane 0 of warp w stores (and re-fills) staging chunk w
+		uint8_t* my_chunk0 = stg + warp * STG_CHUNK_BYTES;
+		auto bias_of = [&](int e, int n0, int ti0) {       // bias + per-image vector of staged element e
+			const int im_l = e / p.BN, c = e - im_l * p.BN, col = n0 + c;
+			float v = 0.f;
+			if (col < p.N) {
+				if (p.bias) v = __ldg(p.bias + col);
+				if (p.rowvec) {
+					const long long im = min((long long)(p.conv ? ti0 + im_l : 0), (long long)p.n_img - 1);
+					const long long o = im * p.rowvec_stride + col;
+					v += p.rowvec_dt == DT_F16 ? __half2float(((const __half*)p.rowvec)[o]) : ((const float*)p.rowvec)[o];
 				}
 			}
-			if (!p.residual && threadIdx.x == 0) tma_store_wait_read();    // with a residual the wait happened before its load
-			asm volatile("bar.sync 1, 128;" ::: "memory");
-			const float* my_vec = epi_vec + (n_img_tile > 1 ? ii * p.BN : 0);
-
+			return v;
+		};
+		auto res_load = [&](int tile, uint32_t sbuf) {     // chunk owners: residual chunk of `tile` -> staging tile sbuf
+			int n0, m0, tw0, th0, ti0; tile_coords(tile, n0, m0, tw0, th0, ti0);
+			uint8_t* dst = my_chunk0 + sbuf * stg_bytes;
+			if (p.conv) tma_load_4d(dst, &tmR, res_full, n0 + warp * STG_CHUNK_COLS, tw0, th0, ti0);
+			else tma_load_2d(dst, &tmR, res_full, n0 + warp * STG_CHUNK_COLS, m0);
+		};
+		float bias_next = 0.f;                             // first staged element of the next tile, fetched a tile ahead
+		if (cluster < num_ctiles) {
+			int n0, m0, tw0, th0, ti0; tile_coords(cluster, n0, m0, tw0, th0, ti0);
+			if (has_vec && et < n_img_tile * p.BN) bias_next = bias_of(et, n0, ti0);
+			if (HAS_RES) {
+				if (et == 0) mbar_expect_tx(res_full, (uint32_t)n_chunks * STG_CHUNK_BYTES);
+				if (chunk_owner) res_load(cluster, 0);
+			}
+		}
+		uint32_t lt = 0;
+		for (int tile = cluster; tile < num_ctiles; tile += nclusters, ++lt) {
+			int n0, m0, tw0, th0, ti0; tile_coords(tile, n0, m0, tw0, th0, ti0);
+			const uint32_t buf = lt & 1, sbuf = lt & (uint32_t)(p.n_stg - 1);
+			const uint32_t my_row = my_row0 + sbuf * stg_bytes;
+			uint8_t* my_chunk = my_chunk0 + sbuf * stg_bytes;
+			const int next = tile + nclusters;
+			#define GEMM_TR(ev) do { if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && lt < 16) p.trace[lt * 8 + (ev)] = clock64(); } while (0)
+			GEMM_TR(0);
+			// stage bias (+ per-image vector) of this tile's columns
+			if (has_vec) {
+				if (et < n_img_tile * p.BN) epi_vec[et] = bias_next;
+				for (int e = et + 256; e < n_img_tile * p.BN; e += 256) epi_vec[e] = bias_of(e, n0, ti0);
+			}
+			// the previous tile's stores must have left the staging tile (with a residual the owners waited before re-filling it)
+			if (!HAS_RES && chunk_owner) { if (p.n_stg == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
+			asm volatile("bar.sync 1, 256;" ::: "memory");
+			if (has_vec && next < num_ctiles && et < n_img_tile * p.BN) {
+				int n1, m1, tw1, th1, ti1; tile_coords(next, n1, m1, tw1, th1, ti1);
+				bias_next = bias_of(et, n1, ti1);          // in flight during the tile
+			}
+			const uint32_t my_vec = smem_u32(epi_vec) + (n_img_tile > 1 ? ii * p.BN : 0) * 4;
+			GEMM_TR(1);
 			mbar_wait(&acc_full[buf], (lt >> 1) & 1);
-			if (p.residual) mbar_wait(res_full, lt & 1);
+			if (HAS_RES) mbar_wait(res_full, lt & 1);
 			tc_fence_after();
+			GEMM_TR(2);
 			const uint32_t trow = tmem_base + buf * 256 + lane_off;
 			auto process = [&](const uint32_t* v, int c0) {
 				float f[16];
@@ -446,18 +520,20 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 				for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
 				if (has_vec) {
 					#pragma unroll
-					for (int j = 0; j < 16; j += 4) { float4 t = *reinterpret_cast<const float4*>(my_vec + c0 + j); f[j] += t.x; f[j+1] += t.y; f[j+2] += t.z; f[j+3] += t.w; }
+					for (int j = 0; j < 16; j += 4) { const float4 t = lds128f(my_vec + (c0 + j) * 4); f[j] += t.x; f[j+1] += t.y; f[j+2] += t.z; f[j+3] += t.w; }
 				}
-				if (p.act != U_NONE) {
+				if (ACT == 1) {
+					#pragma unroll
+					for (int j = 0; j < 16; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-f[j]));
+				} else if (ACT == 2) {
 					#pragma unroll
 					for (int j = 0; j < 16; ++j) f[j] = act_apply_tc(p.act, f[j]);
 				}
-				uint8_t* chunk = my_row + (c0 / STG_CHUNK_COLS) * STG_CHUNK_BYTES;
+				const uint32_t chunk = my_row + (uint32_t)(c0 / STG_CHUNK_COLS) * STG_CHUNK_BYTES;
 				const uint32_t u0 = (uint32_t)((c0 % STG_CHUNK_COLS) >> 3);     // 0 or 2
-				uint4* s0 = reinterpret_cast<uint4*>(chunk + ((u0 ^ row_sw) << 4));
-				uint4* s1 = reinterpret_cast<uint4*>(chunk + (((u0 + 1) ^ row_sw) << 4));
-				if (p.residual) {
-					const uint4 ra = *s0, rb = *s1;
+				const uint32_t s0 = chunk + ((u0 ^ row_sw) << 4), s1 = chunk + (((u0 + 1) ^ row_sw) << 4);
+				if (HAS_RES) {
+					const uint4 ra = lds128(s0), rb = lds128(s1);
 					const __half2* ha = reinterpret_cast<const __half2*>(&ra); const __half2* hb = reinterpret_cast<const __half2*>(&rb);
 					#pragma unroll
 					for (int j = 0; j < 4; ++j) { float2 x = __half22float2(ha[j]), y = __half22float2(hb[j]);
@@ -466,43 +542,48 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 				uint4 a, b; __half2* pa = reinterpret_cast<__half2*>(&a); __half2* pb = reinterpret_cast<__half2*>(&b);
 				#pragma unroll
 				for (int j = 0; j < 4; ++j) { pa[j] = __floats2half2_rn(f[2*j], f[2*j+1]); pb[j] = __floats2half2_rn(f[8+2*j], f[8+2*j+1]); }
-				*s0 = a; *s1 = b;
+				sts128(s0, a); sts128(s1, b);
 			};
 			// 16 accumulator columns at a time, the next tcgen05.ld in flight while the current ones are processed
-			uint32_t va[16], vb[16];
-			tmem_ld16(trow, va);
-			for (int c0 = 0; c0 < p.BN; c0 += 32) {
-				tmem_ld_wait();
-				if (c0 + 16 < p.BN) tmem_ld16(trow + (uint32_t)(c0 + 16), vb);
-				process(va, c0);
-				if (c0 + 16 < p.BN) {
+			if (c_lo < c_hi) {
+				uint32_t va[16], vb[16];
+				tmem_ld16(trow + (uint32_t)c_lo, va);
+				for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
 					tmem_ld_wait();
-					if (c0 + 32 < p.BN) tmem_ld16(trow + (uint32_t)(c0 + 32), va);
-					process(vb, c0 + 16);
+					if (c0 + 16 < c_hi) tmem_ld16(trow + (uint32_t)(c0 + 16), vb);
+					process(va, c0);
+					if (c0 + 16 < c_hi) {
+						tmem_ld_wait();
+						if (c0 + 32 < c_hi) tmem_ld16(trow + (uint32_t)(c0 + 32), va);
+						process(vb, c0 + 16);
+					}
 				}
 			}
+			GEMM_TR(3);
 			// accumulator drained: hand the TMEM buffer back to the MMA warp (one arrival per warp)
 			tc_fence_before();
 			__syncwarp();
 			if (lane == 0) mbar_arrive(&acc_empty[buf]);
 			fence_proxy_async();                           // staging writes -> visible to the TMA (async proxy)
-			asm volatile("bar.sync 1, 128;" ::: "memory");
-			if (threadIdx.x == 0) {
-				for (int c = 0; c < n_chunks; ++c) {
-					if (n0 + c * STG_CHUNK_COLS >= p.N) break;
-					if (p.conv) tma_store_4d(&tmC, stg + c * STG_CHUNK_BYTES, n0 + c * STG_CHUNK_COLS, tw0, th0, ti0);
-					else tma_store_2d(&tmC, stg + c * STG_CHUNK_BYTES, n0 + c * STG_CHUNK_COLS, m0);
+			asm volatile("bar.sync 1, 256;" ::: "memory");
+			GEMM_TR(4);
+			if (HAS_RES && et == 0 && next < num_ctiles) mbar_expect_tx(res_full, (uint32_t)n_chunks * STG_CHUNK_BYTES);
+			if (chunk_owner) {
+				if (n0 + warp * STG_CHUNK_COLS < p.N) {
+					if (p.conv) tma_store_4d(&tmC, my_chunk, n0 + warp * STG_CHUNK_COLS, tw0, th0, ti0);
+					else tma_store_2d(&tmC, my_chunk, n0 + warp * STG_CHUNK_COLS, m0);
 				}
 				tma_store_commit();
-				const int next = tile + gridDim.x;
-				if (p.residual && next < p.num_tiles) { tma_store_wait_read(); issue_res_load(next); }
+				if (HAS_RES && next < num_ctiles) { if (p.n_stg == 2) tma_store_wait_read1(); else tma_store_wait_read(); res_load(next, (lt + 1) & (uint32_t)(p.n_stg - 1)); }
 			}
+			GEMM_TR(5);
 		}
-		if (threadIdx.x == 0) tma_store_wait_all();
+		if (chunk_owner) tma_store_wait_all();
 	}
 	tc_fence_before();
 	__syncthreads();
-	if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+	if (csize > 1) cluster_sync_all();                 // no CTA leaves while a peer may still signal its barriers
+	if (warp == 9) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 // ------------------------------------------------------------------ host side
@@ -584,22 +665,38 @@ static bool persistent_eligible(const GemmParams& p, const GemmEpilogue& ep)
 	return true;
 }
 
-// N tile of the persistent kernel: minimise waves x per-tile cycles. Per tile the tensor pipe needs
-// num_kb * 4 MMAs of max(BN/2 [tcgen05 floor], 32 + BN/4 [A+B shared-memory reads at 128 B/clk]) cycles; the
-// operand tiles cost (128 + BN) * 128 B per k-block from L2 at ~58 B/clk per SM when all SMs pull (measured
-// ~17 TB/s chip-wide); the epilogue (~5 cycles per column) overlaps the next tile unless it is the longest.
-static int pick_bn_persistent(int64_t m_tiles, int64_t N, int num_kb, int sm_count)
+// How many clusters of `csize` CTAs (1 CTA per SM, ~200 KB shared memory each) the device can hold at once.
+static int max_active_clusters(int csize, int sm_count);
+
+// Tile / cluster choice of the persistent kernel: minimise waves x per-tile cycles. Per tile
+//   tensor pipe : num_kb * 4 MMAs of max(BN/2 [tcgen05 floor], 32 + BN/4 [A+B shared-memory reads at 128 B/clk]) cycles
+//   L2 -> SM    : (128/cn + BN/cm) * 128 B per k-block and CTA at ~58 B/clk per SM when every SM pulls (measured
+//                 ~17 TB/s chip-wide): a lone 128 x 256 tile is L2-bound at ~60 % of the tensor peak, which is what the
+//                 cm x cn cluster with TMA multicast removes
+//   epilogue    : ~5 cycles per column, overlaps the next tile unless it is the longest of the three.
+struct TileChoice { int bn, cm, cn; };
+static TileChoice pick_tiles_persistent(int64_t m_tiles, int64_t N, int num_kb, int sm_count)
 {
-	int best = 0; double best_cost = 1e30;
-	for (int bn = 256; bn >= 16; bn -= 16) {
-		if (bn - 16 >= N) continue;
-		const int64_t n_tiles = (N + bn - 1) / bn;
-		if (n_tiles > 1 && (bn % STG_CHUNK_COLS)) continue;       // staging chunks must not straddle tiles
-		const int64_t tiles = n_tiles * m_tiles, waves = (tiles + sm_count - 1) / sm_count;
-		const double mma = (double)num_kb * 4 * std::max(bn / 2.0, 32.0 + bn / 4.0), epi = 250.0 + 5.0 * bn;
-		const double l2 = (double)num_kb * (128.0 + bn) * 128.0 / 58.0;
-		const double cost = (double)waves * std::max(std::max(mma, l2), epi) + epi;
-		if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+	static const int cands[][2] = { {1, 1}, {2, 1}, {1, 2}, {2, 2}, {4, 1}, {4, 2} };
+	const char* e = getenv("GGML_B200_GEMM_CLUSTER");
+	const int max_cluster = e && *e ? atoi(e) : 8;
+	TileChoice best = {0, 1, 1}; double best_cost = 1e30;
+	for (auto& c : cands) {
+		const int cm = c[0], cn = c[1], cs = cm * cn;
+		if (cs > max_cluster || cm > m_tiles) continue;
+		const int nclusters = cs == 1 ? sm_count : max_active_clusters(cs, sm_count);
+		if (nclusters <= 0) continue;
+		for (int bn = 256; bn >= 16; bn -= 16) {
+			if (bn - 16 >= N) continue;
+			const int64_t n_tiles = (N + bn - 1) / bn;
+			if (n_tiles > 1 && (bn % STG_CHUNK_COLS)) continue;       // staging chunks must not straddle tiles
+			if (cn > n_tiles || (bn % (8 * cm))) continue;            // B slices are whole 8-row swizzle atoms
+			const int64_t ctiles = ((m_tiles + cm - 1) / cm) * ((n_tiles + cn - 1) / cn), waves = (ctiles + nclusters - 1) / nclusters;
+			const double mma = (double)num_kb * 4 * std::max(bn / 2.0, 32.0 + bn / 4.0), epi = 250.0 + 5.0 * bn;
+			const double l2 = (double)num_kb * (128.0 / cn + (double)bn / cm) * 128.0 / 58.0;
+			const double cost = ((double)waves * std::max(std::max(mma, l2), epi) + epi) * (1.0 + 0.01 * (cs - 1));   // ties -> smaller cluster
+			if (cost < best_cost - 1e-9) { best_cost = cost; best = {bn, cm, cn}; }
+		}
 	}
 	return best;
 }
@@ -607,15 +704,33 @@ static int pick_bn_persistent(int64_t m_tiles, int64_t N, int num_kb, int sm_cou
 static void finish_setup_persistent(GemmTC* g, const GemmEpilogue& ep, int64_t m_tiles, int sm_count)
 {
 	GemmParams& p = g->p;
-	p.BN = pick_bn_persistent(m_tiles, p.N, p.num_kb, sm_count);
+	TileChoice tc = pick_tiles_persistent(m_tiles, p.N, p.num_kb, sm_count);
+	if (const char* f = getenv("GGML_B200_GEMM_FORCE")) {      // "bn,cm,cn": tuning experiments (tools/gemm_bench.py)
+		int bn = 0, cm = 1, cn = 1;
+		if (sscanf(f, "%d,%d,%d", &bn, &cm, &cn) == 3 && bn >= 16 && bn <= 256 && bn % 16 == 0 && bn % (8 * cm) == 0 &&
+			(bn % STG_CHUNK_COLS == 0 || bn >= p.N) && cm * cn <= 8 && max_active_clusters(cm * cn, sm_count) > 0) tc = {bn, cm, cn};
+	}
+	if (getenv("GGML_B200_GEMM_TRACE")) { CUDA_CHECK(cudaMalloc(&p.trace, 16 * 8 * 8)); CUDA_CHECK(cudaMemset(p.trace, 0, 16 * 8 * 8)); }
+	if (getenv("GGML_B200_GEMM_DEBUG"))
+		B200_LOG("gemm M=%d N=%d K=%d conv=%d m_tiles=%lld -> BN=%d cluster %dx%d", p.M, p.N, p.K, p.conv, (long long)m_tiles, tc.bn, tc.cm, tc.cn);
+	p.BN = tc.bn; p.cm = tc.cm; p.cn = tc.cn;
 	p.m_tiles = (int)m_tiles; p.n_tiles = (p.N + p.BN - 1) / p.BN; p.num_tiles = p.m_tiles * p.n_tiles;
+	p.m_ctiles = (p.m_tiles + p.cm - 1) / p.cm; p.n_ctiles = (p.n_tiles + p.cn - 1) / p.cn;
+	p.a_rows = BM / p.cn; p.b_rows = p.BN / p.cm;
 	const size_t stage = (size_t)BM * BK * 2 + (size_t)p.BN * BK * 2;
 	const size_t n_chunks = (p.BN + STG_CHUNK_COLS - 1) / STG_CHUNK_COLS;
-	const size_t fixed = 1024 + n_chunks * STG_CHUNK_BYTES + (size_t)P_EPI_MAX_IMG * 256 * 4 + (2 * MAX_STAGES + 5) * 8 + 64;
+	// A second staging tile lets the TMA store of tile i drain while tile i+1 is written, but the operand ring needs
+	// ~150 KB in flight to cover the ~2500-cycle loaded L2 latency at 57 B/clk: only take it when 5 stages still fit.
+	p.n_stg = 1;
+	auto fixed_bytes = [&](int n_stg) { return 1024 + n_stg * n_chunks * STG_CHUNK_BYTES + (size_t)P_EPI_MAX_IMG * 256 * 4 + (2 * MAX_STAGES + 5) * 8 + 64; };
+	if ((227 * 1024 - fixed_bytes(2)) / stage >= 5) p.n_stg = 2;
+	const size_t fixed = fixed_bytes(p.n_stg);
 	int stages = (int)std::min<size_t>(MAX_STAGES, (227 * 1024 - fixed) / stage);
 	p.stages = std::max(2, stages);
 	g->smem = fixed + p.stages * stage;
-	g->grid = dim3((unsigned)std::min<int64_t>(p.num_tiles, sm_count));
+	const int cs = p.cm * p.cn;
+	const int nclusters = (int)std::min<int64_t>((int64_t)p.m_ctiles * p.n_ctiles, cs == 1 ? sm_count : max_active_clusters(cs, sm_count));
+	g->grid = dim3((unsigned)(nclusters * cs));
 	g->persistent = true;
 	p.bias = ep.bias; p.rowvec = ep.rowvec; p.rowvec_dt = ep.rowvec_dt; p.rowvec_stride = ep.rowvec_stride;
 	p.rows_per_image = ep.rows_per_image > 0 ? ep.rows_per_image : 1;
@@ -641,10 +756,10 @@ GemmTC* gemm_tc_prepare(const __half* A, int64_t lda, const __half* B, int64_t l
 		if (ep.residual) encode_map(&g->tmR, ep.residual, 2, dc, sc, bc, CU_TENSOR_MAP_SWIZZLE_64B);
 	} else finish_setup(g, ep, m_tiles, sm_count);
 	cuuint64_t da[2] = { (cuuint64_t)K, (cuuint64_t)M }, sa[1] = { (cuuint64_t)lda * 2 };
-	cuuint32_t ba[2] = { BK, BM };
+	cuuint32_t ba[2] = { BK, (cuuint32_t)(g->persistent ? p.a_rows : BM) };
 	encode_map(&g->tmA, A, 2, da, sa, ba);
 	cuuint64_t db[2] = { (cuuint64_t)K, (cuuint64_t)N }, sb[1] = { (cuuint64_t)ldb * 2 };
-	cuuint32_t bb[2] = { BK, (cuuint32_t)p.BN };
+	cuuint32_t bb[2] = { BK, (cuuint32_t)(g->persistent ? p.b_rows : p.BN) };
 	encode_map(&g->tmB, B, 2, db, sb, bb);
 	return g;
 }
@@ -689,11 +804,42 @@ GemmTC* conv3x3_tc_prepare(const __half* x, int64_t n_img, int64_t H, int64_t W,
 	cuuint64_t da[4] = { (cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img };
 	cuuint64_t sa[3] = { (cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2 };
 	cuuint32_t ba[4] = { BK, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bi };
+	if (g->persistent && p.cn > 1) {
+		// each CTA of a cluster row fetches 1/cn of the tile's pixels: split the slowest box dim that is wide enough
+		// (rows of the tile are ordered image, row, column, so such a slice is a contiguous block of tile rows)
+		if (p.bi >= p.cn) { p.a_split_dim = 3; p.a_split_ext = p.bi / p.cn; ba[3] = p.a_split_ext; }
+		else if (p.bh >= p.cn) { p.a_split_dim = 2; p.a_split_ext = p.bh / p.cn; ba[2] = p.a_split_ext; }
+		else { p.a_split_dim = 1; p.a_split_ext = p.bw / p.cn; ba[1] = p.a_split_ext; }
+	}
 	encode_map(&g->tmA, x, 4, da, sa, ba);
 	cuuint64_t db[2] = { (cuuint64_t)(9 * Cin), (cuuint64_t)Cout }, sb[1] = { (cuuint64_t)(9 * Cin) * 2 };
-	cuuint32_t bb[2] = { BK, (cuuint32_t)p.BN };
+	cuuint32_t bb[2] = { BK, (cuuint32_t)(g->persistent ? p.b_rows : p.BN) };
 	encode_map(&g->tmB, Wt, 2, db, sb, bb);
 	return g;
+}
+
+typedef void (*PersistentKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
+static PersistentKernel persistent_variant(const GemmParams& p)
+{
+	const int act = p.act == U_NONE ? 0 : p.act == U_SILU ? 1 : 2;
+	const bool res = p.residual != nullptr;
+	switch (act * 2 + (res ? 1 : 0)) {
+	case 0: return gemm_tc_persistent_kernel<0, false>;
+	case 1: return gemm_tc_persistent_kernel<0, true>;
+	case 2: return gemm_tc_persistent_kernel<1, false>;
+	case 3: return gemm_tc_persistent_kernel<1, true>;
+	case 4: return gemm_tc_persistent_kernel<2, false>;
+	default: return gemm_tc_persistent_kernel<2, true>;
+	}
+}
+static void persistent_attrs_once()
+{
+	static bool done = false;
+	if (done) return;
+	done = true;
+	PersistentKernel ks[] = { gemm_tc_persistent_kernel<0, false>, gemm_tc_persistent_kernel<0, true>, gemm_tc_persistent_kernel<1, false>,
+		gemm_tc_persistent_kernel<1, true>, gemm_tc_persistent_kernel<2, false>, gemm_tc_persistent_kernel<2, true> };
+	for (PersistentKernel k : ks) CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 }
 
 void gemm_tc_launch(cudaStream_t s, GemmTC* g)
@@ -701,14 +847,55 @@ void gemm_tc_launch(cudaStream_t s, GemmTC* g)
 	static bool attr_set = false;
 	if (!attr_set) {
 		CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-		CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		attr_set = true;
 	}
-	if (g->persistent) gemm_tc_persistent_kernel<<<g->grid, P_THREADS, g->smem, s>>>(g->tmA, g->tmB, g->tmC, g->tmR, g->p);
-	else gemm_tc_kernel<<<g->grid, 192, g->smem, s>>>(g->tmA, g->tmB, g->p);
+	if (g->persistent) {
+		persistent_attrs_once();
+		const int cs = g->p.cm * g->p.cn;
+		cudaLaunchConfig_t cfg = {};
+		cfg.gridDim = g->grid; cfg.blockDim = dim3(P_THREADS); cfg.dynamicSmemBytes = g->smem; cfg.stream = s;
+		cudaLaunchAttribute at[1];
+		at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+		cfg.attrs = at; cfg.numAttrs = cs > 1 ? 1 : 0;
+		CUDA_CHECK(cudaLaunchKernelEx(&cfg, persistent_variant(g->p), g->tmA, g->tmB, g->tmC, g->tmR, g->p));
+	} else gemm_tc_kernel<<<g->grid, 192, g->smem, s>>>(g->tmA, g->tmB, g->p);
 	g_stats.kernel_launches++;
 }
 
-void gemm_tc_free(GemmTC* g) { delete g; }
+static int max_active_clusters(int csize, int sm_count)
+{
+	static int cache[17] = {0};
+	if (csize < 1 || csize > 16) return 0;
+	if (cache[csize]) return cache[csize];
+	persistent_attrs_once();
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned)(sm_count / csize * csize)); cfg.blockDim = dim3(P_THREADS); cfg.dynamicSmemBytes = 200 * 1024;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+	cfg.attrs = at; cfg.numAttrs = 1;
+	int n = 0;
+	cudaError_t e = cudaOccupancyMaxActiveClusters(&n, gemm_tc_persistent_kernel<0, false>, &cfg);
+	if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+	n = std::min(n, sm_count / csize);
+	cache[csize] = n > 0 ? n : -1;
+	return cache[csize];
+}
+
+void gemm_tc_free(GemmTC* g)
+{
+	if (g->p.trace) {
+		long long h[16 * 8];
+		cudaDeviceSynchronize();
+		cudaMemcpy(h, g->p.trace, sizeof(h), cudaMemcpyDeviceToHost);
+		fprintf(stderr, "[ggml_b200] epilogue timeline of CTA 0 (cycles since its first tile; M=%d N=%d K=%d BN=%d): start | bias+store-drain+bar | acc ready | drained | fence+bar | stores issued\n", g->p.M, g->p.N, g->p.K, g->p.BN);
+		for (int t = 0; t < 16 && h[t * 8]; ++t) {
+			fprintf(stderr, "  tile %2d:", t);
+			for (int e = 0; e < 6; ++e) fprintf(stderr, " %8lld", h[t * 8 + e] - h[0]);
+			fprintf(stderr, "\n");
+		}
+		cudaFree(g->p.trace);
+	}
+	delete g;
+}
 
 }  // namespace b200

@@ -11,6 +11,9 @@ void k_binary(cudaStream_t s, BinOp op, const View& dst, const View& a, const Vi
 void k_unary(cudaStream_t s, UnaryOp op, float param, const View& dst, const View& src);
 void k_upscale(cudaStream_t s, const View& dst, const View& src);
 void k_softmax_rows(cudaStream_t s, const View& dst, const View& src, bool causal, int n_past);
+// rows of f32 scores -> f16 probabilities softmax(scale * s) (wide-head attention as two tensor-core GEMMs)
+bool k_softmax_f32_f16_supported(int64_t cols);
+void k_softmax_f32_f16(cudaStream_t s, const float* scores, __half* probs, int64_t rows, int64_t cols, int64_t ld_s, int64_t ld_p, float scale);
 void k_get_rows(cudaStream_t s, const View& dst, const View& table, const View& ids);
 void k_timestep_embedding(cudaStream_t s, const View& dst, const View& ts, int dim, int max_period);
 void k_gemm_simt(cudaStream_t s, const View& c, const View& a, const View& b, bool round_b_f16);

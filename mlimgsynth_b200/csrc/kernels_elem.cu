@@ -235,6 +235,68 @@ void k_softmax_rows(cudaStream_t s, const View& dst, const View& src, bool causa
 	g_stats.kernel_launches++;
 }
 
+// ------------------------------------------------------------------ scaled row softmax, f32 scores -> f16 probabilities
+// (the wide-head attention path: S = QK^T and O = PV run as tensor-core GEMMs, planner.cpp). One block per row, the row
+// lives in registers (NV x 4 floats per thread): one read of the scores, one write of the probabilities.
+template <int NV>
+__global__ void softmax_f32_f16_kernel(const float* __restrict__ sc, __half* __restrict__ pr, int cols, long long ld_s, long long ld_p, float scale_log2)
+{
+	const float* row = sc + blockIdx.x * ld_s;
+	__half* out = pr + blockIdx.x * ld_p;
+	__shared__ float red[32];
+	float4 v[NV];
+	float mx = -INFINITY;
+	#pragma unroll
+	for (int i = 0; i < NV; ++i) {
+		const int c = (threadIdx.x + i * blockDim.x) * 4;
+		if (c < cols) { v[i] = *reinterpret_cast<const float4*>(row + c); mx = fmaxf(mx, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w))); }
+	}
+	for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(~0u, mx, o));
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+	__syncthreads();
+	mx = red[0];
+	for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+	__syncthreads();
+	const float m2 = mx * scale_log2;
+	float sum = 0.f;
+	#pragma unroll
+	for (int i = 0; i < NV; ++i) {
+		const int c = (threadIdx.x + i * blockDim.x) * 4;
+		if (c < cols) {
+			v[i].x = exp2f(fmaf(v[i].x, scale_log2, -m2)); v[i].y = exp2f(fmaf(v[i].y, scale_log2, -m2));
+			v[i].z = exp2f(fmaf(v[i].z, scale_log2, -m2)); v[i].w = exp2f(fmaf(v[i].w, scale_log2, -m2));
+			sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+		}
+	}
+	for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(~0u, sum, o);
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+	__syncthreads();
+	sum = 0.f;
+	for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += red[w];
+	const float inv = 1.0f / sum;
+	#pragma unroll
+	for (int i = 0; i < NV; ++i) {
+		const int c = (threadIdx.x + i * blockDim.x) * 4;
+		if (c < cols) {
+			__half2 a = __floats2half2_rn(v[i].x * inv, v[i].y * inv), b = __floats2half2_rn(v[i].z * inv, v[i].w * inv);
+			uint2 o2; o2.x = *reinterpret_cast<uint32_t*>(&a); o2.y = *reinterpret_cast<uint32_t*>(&b);
+			*reinterpret_cast<uint2*>(out + c) = o2;
+		}
+	}
+}
+bool k_softmax_f32_f16_supported(int64_t cols) { return cols % 4 == 0 && cols <= 256 * 4 * 16; }
+void k_softmax_f32_f16(cudaStream_t s, const float* scores, __half* probs, int64_t rows, int64_t cols, int64_t ld_s, int64_t ld_p, float scale)
+{
+	const float sl2 = scale * 1.4426950408889634f;
+	const int nv = (int)((cols / 4 + 255) / 256);
+	if (nv <= 1) softmax_f32_f16_kernel<1><<<(unsigned)rows, 256, 0, s>>>(scores, probs, (int)cols, ld_s, ld_p, sl2);
+	else if (nv <= 2) softmax_f32_f16_kernel<2><<<(unsigned)rows, 256, 0, s>>>(scores, probs, (int)cols, ld_s, ld_p, sl2);
+	else if (nv <= 4) softmax_f32_f16_kernel<4><<<(unsigned)rows, 256, 0, s>>>(scores, probs, (int)cols, ld_s, ld_p, sl2);
+	else if (nv <= 8) softmax_f32_f16_kernel<8><<<(unsigned)rows, 256, 0, s>>>(scores, probs, (int)cols, ld_s, ld_p, sl2);
+	else softmax_f32_f16_kernel<16><<<(unsigned)rows, 256, 0, s>>>(scores, probs, (int)cols, ld_s, ld_p, sl2);
+	g_stats.kernel_launches++;
+}
+
 // ------------------------------------------------------------------ get_rows (clip.c:338)
 __global__ void get_rows_kernel(V4 dst, V4 table, V4 ids)
 {

@@ -39,7 +39,7 @@ struct PT {                 // planned tensor: strided view over a buffer
 
 enum StepKind {
 	S_COPY, S_BINARY, S_UNARY, S_UPSCALE, S_SOFTMAX, S_GET_ROWS, S_TSEMB, S_GEMM_SIMT,
-	S_GROUPNORM, S_LAYERNORM, S_GEGLU, S_IM2COL, S_WPREP_CONV, S_ATTENTION, S_GEMM_TC, S_CONV_TC, S_ZERO,
+	S_GROUPNORM, S_LAYERNORM, S_GEGLU, S_IM2COL, S_WPREP_CONV, S_ATTENTION, S_GEMM_TC, S_CONV_TC, S_ZERO, S_SOFTMAX_F16,
 };
 
 struct Step {
@@ -436,6 +436,41 @@ bool Builder::try_attention(ggml_tensor* t)
 	PT pq = get(q), pk = get(k), pvv = get(v);
 	// broadcast of k/v over q's batch dims is not used by the reference
 	if (k->ne[2] != q->ne[2] || k->ne[3] != q->ne[3]) return false;
+	// Wide heads (the VAE's single 512-wide head, vae.c:46-74) do not fit the fused kernel's tensor-memory budget:
+	// run them as two tensor-core GEMMs around a register-resident row softmax, per (head, image):
+	//   S[nq,nk] (f32) = Q K^T ;  P (f16) = softmax(scale * S) ;  O[nq,d] = P (V^T)^T  with V^T materialised once.
+	const int64_t d = q->ne[0], nq = q->ne[1], nk = k->ne[1];
+	if (!force_simt && !causal && d > 160 && d % 8 == 0 && nq >= 128 && nk % 8 == 0 && k_softmax_f32_f16_supported(nk)) {
+		PT A = as_gemm_rows(pq), Bk = as_gemm_rows(pk);
+		PT o; o.dt = DT_F16;
+		o.ne[0] = pv->ne[0]; o.ne[1] = pv->ne[1]; o.ne[2] = pv->ne[2]; o.ne[3] = pv->ne[3];
+		o.st[0] = 1; o.st[2] = o.ne[0]; o.st[1] = o.ne[0] * o.ne[2]; o.st[3] = o.st[1] * o.ne[1];
+		o.buf = new_buf(BUF_ARENA, (size_t)o.numel() * 2);
+		int64_t ne_s[4] = { nk, nq, 1, 1 };
+		PT S = new_pt(DT_F32, ne_s), Pm = new_pt(DT_F16, ne_s);
+		int64_t ne_vt[4] = { nk, d, 1, 1 };
+		PT Vt = new_pt(DT_F16, ne_vt);
+		for (int64_t b = 0; b < q->ne[3]; ++b) for (int64_t h = 0; h < q->ne[2]; ++h) {
+			PT qa = A, ka = Bk, va = pvv, oa = o;
+			qa.off += h * A.st[2] + b * A.st[3]; ka.off += h * Bk.st[2] + b * Bk.st[3];
+			va.off += h * pvv.st[2] + b * pvv.st[3]; oa.off += h * o.st[2] + b * o.st[3];
+			for (PT* x : { &qa, &ka, &va, &oa }) { x->ne[2] = x->ne[3] = 1; }
+			Step g1; g1.kind = S_GEMM_TC; g1.name = "attn_qk";
+			g1.in[0] = qa; g1.in[1] = ka; g1.n_in = 2; g1.out = S;
+			g1.M = nq; g1.N = nk; g1.K = d; g1.lda = A.st[1]; g1.ldb = Bk.st[1]; g1.ldc = nk;
+			P->steps.push_back(g1);
+			Step& sm2 = emit(S_SOFTMAX_F16, "attn_softmax");
+			sm2.out = Pm; sm2.in[0] = S; sm2.n_in = 1; sm2.fparam = scale;
+			copy(Vt, va, "attn_v_transpose");          // [nk, d] view of token-major V -> rows of nk keys per channel
+			Step g2; g2.kind = S_GEMM_TC; g2.name = "attn_pv";
+			g2.in[0] = Pm; g2.in[1] = Vt; g2.n_in = 2; g2.out = oa;
+			g2.M = nq; g2.N = d; g2.K = nk; g2.lda = nk; g2.ldb = nk; g2.ldc = o.st[1];
+			P->steps.push_back(g2);
+		}
+		done[t] = done[sc] = done[sm] = true;
+		finish(pv, o);
+		return true;
+	}
 	// output [d, nq, H, B]; choose token-major, heads interleaved: (d:1, H:d, nq:d*H, B:d*H*nq) so that
 	// the reference's head-merge permute+cont+reshape becomes a free view
 	PT o; o.dt = DT_F16;
@@ -893,6 +928,9 @@ static void run_step(Plan* P, Step& s, cudaStream_t st)
 	case S_BINARY: k_binary(st, (BinOp)s.iop, view_of(P, s.out), view_of(P, s.in[0]), view_of(P, s.in[1])); break;
 	case S_UNARY: k_unary(st, (UnaryOp)s.iop, s.fparam, view_of(P, s.out), view_of(P, s.in[0])); break;
 	case S_UPSCALE: k_upscale(st, view_of(P, s.out), view_of(P, s.in[0])); break;
+	case S_SOFTMAX_F16:
+		k_softmax_f32_f16(st, (const float*)buf_ptr(P, s.in[0]), (__half*)buf_ptr(P, s.out), s.in[0].ne[1], s.in[0].ne[0], s.in[0].ne[0], s.out.ne[0], s.fparam);
+		break;
 	case S_SOFTMAX: k_softmax_rows(st, view_of(P, s.out), view_of(P, s.in[0]), s.iparam[0] != 0, s.iparam[1]); break;
 	case S_GET_ROWS: k_get_rows(st, view_of(P, s.out), view_of(P, s.in[0]), view_of(P, s.in[1])); break;
 	case S_TSEMB: k_timestep_embedding(st, view_of(P, s.out), view_of(P, s.in[0]), s.iparam[0], s.iparam[1]); break;
@@ -946,7 +984,7 @@ static void run_step(Plan* P, Step& s, cudaStream_t st)
 static void dump_plan(Plan* P)
 {
 	static const char* kn[] = { "COPY", "BINARY", "UNARY", "UPSCALE", "SOFTMAX", "GET_ROWS", "TSEMB", "GEMM_SIMT",
-		"GROUPNORM", "LAYERNORM", "GEGLU", "IM2COL", "WPREP_CONV", "ATTENTION", "GEMM_TC", "CONV_TC", "ZERO" };
+		"GROUPNORM", "LAYERNORM", "GEGLU", "IM2COL", "WPREP_CONV", "ATTENTION", "GEMM_TC", "CONV_TC", "ZERO", "SOFTMAX_F16" };
 	std::map<std::string, int> hist;
 	for (Step& s : P->steps) hist[kn[s.kind]]++;
 	std::string line;

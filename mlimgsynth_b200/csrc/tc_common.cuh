@@ -44,6 +44,15 @@ __device__ __forceinline__ bool elect_one()
 __device__ __forceinline__ int warp_id_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 __device__ __forceinline__ uint32_t uniform_u32(uint32_t x) { return __shfl_sync(0xffffffffu, x, 0); }
 
+// Explicit shared-space accesses: pointers carved out of the aligned dynamic shared memory block are generic to the
+// compiler (LD.E / ST.E with 64-bit address math); these keep them on the LDS / STS path.
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{ uint4 v; asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)); return v; }
+__device__ __forceinline__ float4 lds128f(uint32_t addr)
+{ float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr)); return v; }
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v)
+{ asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
