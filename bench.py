@@ -166,7 +166,7 @@ def main():
         dist.barrier()
     model = weights_path("sd1")
 
-    from mlimgsynth_b200 import api
+    from mlimgsynth_b200 import api, dist as D
     import ctypes as C
     B = args.batch
     os.environ.setdefault("GGML_B200_QUIET", "1")
@@ -184,7 +184,8 @@ def main():
         return {k: getattr(s, k) for k, _ in St._fields_}
 
     def gen(seed, cached_cond):
-        ctx.set("seed", seed * 1000 + rank * 100)
+        # image i of the global batch gets seed + i whatever the world size; this rank owns a contiguous block
+        ctx.set("seed", D.image_seeds(seed * 1000, B * world, rank, world)[0])
         ctx.set("prompt", PROMPT)
         if cached_cond:
             ctx.set("tensor_use_flags", api.TUF_CONDITIONING)
@@ -197,11 +198,7 @@ def main():
         torch.cuda.synchronize()
 
     def allmax(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return D.all_max(x, device="cuda") if world > 1 else x
 
     # ---- warm-up (builds graphs, uploads weights, captures CUDA graphs)
     for i in range(max(args.warmup, 3)):
@@ -228,9 +225,7 @@ def main():
     for i in range(args.steps):
         imgs = gen(200 + i, cached_cond=False)
         if world > 1:
-            mine = torch.from_numpy(np.stack(imgs)).cuda()
-            out = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
-            dist.gather(mine, out, dst=0)
+            D.gather_arrays(np.stack(imgs), dst=0, device="cuda")     # NCCL: only the final RGB8 images travel
     barrier()
     e2e_s = allmax(time.perf_counter() - t0)
     e1 = stats()

@@ -1,0 +1,87 @@
+"""Multi-GPU plumbing of the denoising path: one process per GPU, no data-path collective.
+
+The path shards only across independent units:
+  * images of a batch -- image i is generated with seed + i and a fresh noise offset (the semantics of the
+    reference's generate.sh:55-61 loop; the reference itself rejects batch > 1, mlimgsynth.c:1640-1641);
+  * VAE decode tiles -- independent given the fixed tile graph (vae.c:343-346); the merged image must be what the
+    reference's serial row-major loop produces: later tiles overwrite earlier ones (vae.c:365-387).
+torch.distributed (NCCL on the GPUs, gloo in the CPU tests) is used for the barrier, max-over-ranks timing and one
+gather of the final images / tiles. Nothing here touches the kernels: ranks never exchange activations.
+"""
+import numpy as np
+
+
+def image_slice(n_images, rank, world):
+    """Contiguous block of image indices owned by `rank` (blocks differ by at most one image)."""
+    base, rem = divmod(n_images, world)
+    start = rank * base + min(rank, rem)
+    return range(start, start + base + (1 if rank < rem else 0))
+
+
+def image_seeds(seed, n_images, rank, world):
+    """Seeds of the images of this rank: image i of the global batch always gets seed + i, whatever the world size."""
+    return [seed + i for i in image_slice(n_images, rank, world)]
+
+
+def tile_grid(full, tile, k):
+    """Tile origins along one axis, as the reference computes them (vae.c:332-391): tile extent `tile` (already
+    including the 2k overlap and clipped to `full`), step tile - 2k, last tile shifted back inside the tensor."""
+    if tile >= full:
+        return [0]
+    step = tile - 2 * k
+    n = (full + step - 1) // step
+    return [min(t * step, full - tile) for t in range(n)]
+
+
+def tile_list(w, h, tw, th, k):
+    """All tiles in the reference's visiting order (row-major: y outer, x inner) as (index, x0, y0)."""
+    out = []
+    for y0 in tile_grid(h, th, k):
+        for x0 in tile_grid(w, tw, k):
+            out.append((len(out), x0, y0))
+    return out
+
+
+def tiles_of_rank(tiles, rank, world):
+    """Round-robin assignment of tiles to ranks."""
+    return [t for t in tiles if t[0] % world == rank]
+
+
+def merge_tiles(canvas, decoded, w, h, tw, th, k, up):
+    """Paste decoded tiles into `canvas` [C, h*up, w*up] in the reference's order so that overlaps resolve identically
+    (the kept region of a tile is [d, d + n - k) with d = k except at the left/top border; vae.c:365-387).
+    `decoded` maps tile index -> array [C, th*up, tw*up]."""
+    for idx, x0, y0 in tile_list(w, h, tw, th, k):
+        t = decoded[idx]
+        d0, d1 = (k if x0 else 0), (k if y0 else 0)
+        c0 = tw if tw == w else tw - k
+        c1 = th if th == h else th - k
+        ys, xs = (y0 + d1) * up, (x0 + d0) * up
+        canvas[:, ys:ys + c1 * up, xs:xs + c0 * up] = t[:, d1 * up:(d1 + c1) * up, d0 * up:(d0 + c0) * up]
+    return canvas
+
+
+def gather_arrays(arr, dst=0, device=None):
+    """Gather equally-shaped numpy arrays from all ranks to rank `dst` (returns the list there, None elsewhere).
+    Works on any initialised torch.distributed backend; with NCCL pass the rank's CUDA device."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return [arr]
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    if device is not None:
+        t = t.to(device)
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())] if dist.get_rank() == dst else None
+    dist.gather(t, out, dst=dst)
+    return [o.cpu().numpy() for o in out] if out is not None else None
+
+
+def all_max(x, device=None):
+    """Max of a Python float over all ranks (timing is reported as the slowest rank's)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(x)
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
