@@ -41,6 +41,7 @@ struct GemmParams {
 	// thread-block cluster of cm x cn CTAs working on cm m-tiles x cn n-tiles: every A tile is loaded once per
 	// cluster row (each of its cn CTAs fetches 1/cn of the rows and TMA-multicasts them), every B tile once per column
 	int cm, cn, a_rows, b_rows, a_split_dim, a_split_ext, m_ctiles, n_ctiles;
+	int geglu;                         // epilogue gates column pairs: output has N/2 columns (weights pre-permuted)
 	int n_stg;                         // staging tiles (2: the TMA store of tile i drains while tile i+1 is written)
 	long long* trace;                  // debug timeline of CTA 0's epilogue (GGML_B200_GEMM_TRACE), null in production
 };
@@ -73,6 +74,13 @@ __device__ __forceinline__ float act_apply_tc(int op, float x)
 	case U_TANH: return tanhf(x);
 	default: return x;
 	}
+}
+
+__device__ __forceinline__ float gelu_tanh_fast(float g)
+{
+	const float u = 0.79788456080286535588f * g * fmaf(0.044715f * g, g, 1.0f);
+	float t; asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+	return 0.5f * g * (1.0f + t);
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -329,7 +337,7 @@ __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile
 __device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_count_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
 
-template <int ACT, bool HAS_RES>     // ACT: 0 none, 1 SiLU, 2 run-time p.act; HAS_RES: f16 residual tile added in the epilogue
+template <int ACT, bool HAS_RES>     // ACT: 0 none, 1 SiLU, 2 run-time p.act, 3 GEGLU gate; HAS_RES: f16 residual tile added in the epilogue
 __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
 	const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmParams p)
@@ -337,7 +345,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 	extern __shared__ __align__(1024) uint8_t smem_raw[];
 	uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 	const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)p.BN * BK * 2, stage_bytes = a_bytes + b_bytes;
-	const int n_chunks = (p.BN + STG_CHUNK_COLS - 1) / STG_CHUNK_COLS;
+	constexpr int ACC_PER_CHUNK = ACT == 3 ? 2 * STG_CHUNK_COLS : STG_CHUNK_COLS;   // accumulator columns behind one staging chunk
+	const int n_chunks = (p.BN + ACC_PER_CHUNK - 1) / ACC_PER_CHUNK;
 	uint8_t* stg = smem + (size_t)p.stages * stage_bytes;                       // staging tile (1024-aligned)
 	float* epi_vec = (float*)(stg + (size_t)p.n_stg * n_chunks * STG_CHUNK_BYTES);   // [P_EPI_MAX_IMG][BN]
 	uint64_t* full_bar  = (uint64_t*)(epi_vec + P_EPI_MAX_IMG * 256);
@@ -454,7 +463,9 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 		const int n_img_tile = (p.conv && p.rowvec) ? p.bi : 1;
 		const int ii = p.conv ? r / (p.bw * p.bh) : 0;     // image of this row inside the tile
 		const int half_chunks = (n_chunks + 1) >> 1;
-		const int c_lo = grp * half_chunks * STG_CHUNK_COLS, c_hi = min(p.BN, (grp + 1) * half_chunks * STG_CHUNK_COLS);
+		const int c_lo = grp * half_chunks * ACC_PER_CHUNK, c_hi = min(p.BN, (grp + 1) * half_chunks * ACC_PER_CHUNK);
+		const int n_out = ACT == 3 ? p.N / 2 : p.N;         // output columns
+		auto out_col0 = [&](int n0) { return (ACT == 3 ? n0 / 2 : n0) + warp * STG_CHUNK_COLS; };   // first output column of this warp's chunk
 		const int et = threadIdx.x;                        // 0..255 among the epilogue threads
 		const bool chunk_owner = lane == 0 && warp < n_chunks;    // lane 0 of warp w stores (and re-fills) staging chunk w
 		uint8_t* my_chunk0 = stg + warp * STG_CHUNK_BYTES;
@@ -544,6 +555,42 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 				for (int j = 0; j < 4; ++j) { pa[j] = __floats2half2_rn(f[2*j], f[2*j+1]); pb[j] = __floats2half2_rn(f[8+2*j], f[8+2*j+1]); }
 				sts128(s0, a); sts128(s1, b);
 			};
+			// GEGLU: 16 value columns and their 16 gate columns -> 16 gated outputs
+			auto process_geglu = [&](const uint32_t* vx, const uint32_t* vg, int c0) {
+				float f[16];
+				#pragma unroll
+				for (int j = 0; j < 16; j += 4) {
+					float4 bx = make_float4(0.f, 0.f, 0.f, 0.f), bg = bx;
+					if (has_vec) { bx = lds128f(my_vec + (c0 + j) * 4); bg = lds128f(my_vec + (c0 + 16 + j) * 4); }
+					f[j]     = (__uint_as_float(vx[j])     + bx.x) * gelu_tanh_fast(__uint_as_float(vg[j])     + bg.x);
+					f[j + 1] = (__uint_as_float(vx[j + 1]) + bx.y) * gelu_tanh_fast(__uint_as_float(vg[j + 1]) + bg.y);
+					f[j + 2] = (__uint_as_float(vx[j + 2]) + bx.z) * gelu_tanh_fast(__uint_as_float(vg[j + 2]) + bg.z);
+					f[j + 3] = (__uint_as_float(vx[j + 3]) + bx.w) * gelu_tanh_fast(__uint_as_float(vg[j + 3]) + bg.w);
+				}
+				const int oc = c0 >> 1;                            // output column inside the tile
+				const uint32_t chunk = my_row + (uint32_t)(oc / STG_CHUNK_COLS) * STG_CHUNK_BYTES;
+				const uint32_t u0 = (uint32_t)((oc % STG_CHUNK_COLS) >> 3);
+				uint4 a, b; __half2* pa = reinterpret_cast<__half2*>(&a); __half2* pb = reinterpret_cast<__half2*>(&b);
+				#pragma unroll
+				for (int j = 0; j < 4; ++j) { pa[j] = __floats2half2_rn(f[2*j], f[2*j+1]); pb[j] = __floats2half2_rn(f[8+2*j], f[8+2*j+1]); }
+				sts128(chunk + ((u0 ^ row_sw) << 4), a); sts128(chunk + (((u0 + 1) ^ row_sw) << 4), b);
+			};
+			if (ACT == 3) {
+				if (c_lo < c_hi) {
+					uint32_t va[16], vb[16], vc[16], vd[16];
+					tmem_ld16(trow + (uint32_t)c_lo, va); tmem_ld16(trow + (uint32_t)(c_lo + 16), vb);
+					for (int c0 = c_lo; c0 < c_hi; c0 += 64) {
+						tmem_ld_wait();
+						if (c0 + 32 < c_hi) { tmem_ld16(trow + (uint32_t)(c0 + 32), vc); tmem_ld16(trow + (uint32_t)(c0 + 48), vd); }
+						process_geglu(va, vb, c0);
+						if (c0 + 32 < c_hi) {
+							tmem_ld_wait();
+							if (c0 + 64 < c_hi) { tmem_ld16(trow + (uint32_t)(c0 + 64), va); tmem_ld16(trow + (uint32_t)(c0 + 80), vb); }
+							process_geglu(vc, vd, c0 + 32);
+						}
+					}
+				}
+			} else
 			// 16 accumulator columns at a time, the next tcgen05.ld in flight while the current ones are processed
 			if (c_lo < c_hi) {
 				uint32_t va[16], vb[16];
@@ -569,9 +616,9 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 			GEMM_TR(4);
 			if (HAS_RES && et == 0 && next < num_ctiles) mbar_expect_tx(res_full, (uint32_t)n_chunks * STG_CHUNK_BYTES);
 			if (chunk_owner) {
-				if (n0 + warp * STG_CHUNK_COLS < p.N) {
-					if (p.conv) tma_store_4d(&tmC, my_chunk, n0 + warp * STG_CHUNK_COLS, tw0, th0, ti0);
-					else tma_store_2d(&tmC, my_chunk, n0 + warp * STG_CHUNK_COLS, m0);
+				if (out_col0(n0) < n_out) {
+					if (p.conv) tma_store_4d(&tmC, my_chunk, out_col0(n0), tw0, th0, ti0);
+					else tma_store_2d(&tmC, my_chunk, out_col0(n0), m0);
 				}
 				tma_store_commit();
 				if (HAS_RES && next < num_ctiles) { if (p.n_stg == 2) tma_store_wait_read1(); else tma_store_wait_read(); res_load(next, (lt + 1) & (uint32_t)(p.n_stg - 1)); }
@@ -662,6 +709,7 @@ static bool persistent_eligible(const GemmParams& p, const GemmEpilogue& ep)
 	if (p.c_dt != DT_F16 || (p.ldc % 8) || ((uintptr_t)p.C & 15)) return false;
 	if (ep.residual && (ep.residual_dt != DT_F16 || ep.ldr != p.ldc || ((uintptr_t)ep.residual & 15))) return false;
 	if (p.conv && ep.rowvec && p.bi > P_EPI_MAX_IMG) return false;
+	if (ep.geglu && (p.conv || ep.residual || ep.rowvec || ep.act != U_NONE || (p.N % 64))) return false;
 	return true;
 }
 
@@ -675,7 +723,7 @@ static int max_active_clusters(int csize, int sm_count);
 //                 cm x cn cluster with TMA multicast removes
 //   epilogue    : ~5 cycles per column, overlaps the next tile unless it is the longest of the three.
 struct TileChoice { int bn, cm, cn; };
-static TileChoice pick_tiles_persistent(int64_t m_tiles, int64_t N, int num_kb, int sm_count)
+static TileChoice pick_tiles_persistent(int64_t m_tiles, int64_t N, int num_kb, int sm_count, bool geglu)
 {
 	static const int cands[][2] = { {1, 1}, {2, 1}, {1, 2}, {2, 2}, {4, 1}, {4, 2} };
 	const char* e = getenv("GGML_B200_GEMM_CLUSTER");
@@ -689,7 +737,8 @@ static TileChoice pick_tiles_persistent(int64_t m_tiles, int64_t N, int num_kb, 
 		for (int bn = 256; bn >= 16; bn -= 16) {
 			if (bn - 16 >= N) continue;
 			const int64_t n_tiles = (N + bn - 1) / bn;
-			if (n_tiles > 1 && (bn % STG_CHUNK_COLS)) continue;       // staging chunks must not straddle tiles
+			if (n_tiles > 1 && (bn % (geglu ? 2 * STG_CHUNK_COLS : STG_CHUNK_COLS))) continue;   // staging chunks must not straddle tiles
+			if (geglu && (bn % 32)) continue;
 			if (cn > n_tiles || (bn % (8 * cm))) continue;            // B slices are whole 8-row swizzle atoms
 			const int64_t ctiles = ((m_tiles + cm - 1) / cm) * ((n_tiles + cn - 1) / cn), waves = (ctiles + nclusters - 1) / nclusters;
 			const double mma = (double)num_kb * 4 * std::max(bn / 2.0, 32.0 + bn / 4.0), epi = 250.0 + 5.0 * bn;
@@ -704,7 +753,8 @@ static TileChoice pick_tiles_persistent(int64_t m_tiles, int64_t N, int num_kb, 
 static void finish_setup_persistent(GemmTC* g, const GemmEpilogue& ep, int64_t m_tiles, int sm_count)
 {
 	GemmParams& p = g->p;
-	TileChoice tc = pick_tiles_persistent(m_tiles, p.N, p.num_kb, sm_count);
+	p.geglu = ep.geglu ? 1 : 0;
+	TileChoice tc = pick_tiles_persistent(m_tiles, p.N, p.num_kb, sm_count, ep.geglu);
 	if (const char* f = getenv("GGML_B200_GEMM_FORCE")) {      // "bn,cm,cn": tuning experiments (tools/gemm_bench.py)
 		int bn = 0, cm = 1, cn = 1;
 		if (sscanf(f, "%d,%d,%d", &bn, &cm, &cn) == 3 && bn >= 16 && bn <= 256 && bn % 16 == 0 && bn % (8 * cm) == 0 &&
@@ -718,7 +768,8 @@ static void finish_setup_persistent(GemmTC* g, const GemmEpilogue& ep, int64_t m
 	p.m_ctiles = (p.m_tiles + p.cm - 1) / p.cm; p.n_ctiles = (p.n_tiles + p.cn - 1) / p.cn;
 	p.a_rows = BM / p.cn; p.b_rows = p.BN / p.cm;
 	const size_t stage = (size_t)BM * BK * 2 + (size_t)p.BN * BK * 2;
-	const size_t n_chunks = (p.BN + STG_CHUNK_COLS - 1) / STG_CHUNK_COLS;
+	const size_t acc_per_chunk = ep.geglu ? 2 * STG_CHUNK_COLS : STG_CHUNK_COLS;
+	const size_t n_chunks = (p.BN + acc_per_chunk - 1) / acc_per_chunk;
 	// A second staging tile lets the TMA store of tile i drain while tile i+1 is written, but the operand ring needs
 	// ~150 KB in flight to cover the ~2500-cycle loaded L2 latency at 57 B/clk: only take it when 5 stages still fit.
 	p.n_stg = 1;
@@ -750,11 +801,14 @@ GemmTC* gemm_tc_prepare(const __half* A, int64_t lda, const __half* B, int64_t l
 	int64_t m_tiles = (M + BM - 1) / BM;
 	if (persistent_eligible(p, ep)) {
 		finish_setup_persistent(g, ep, m_tiles, sm_count);
-		cuuint64_t dc[2] = { (cuuint64_t)N, (cuuint64_t)M }, sc[1] = { (cuuint64_t)ldc * 2 };
+		cuuint64_t dc[2] = { (cuuint64_t)(ep.geglu ? N / 2 : N), (cuuint64_t)M }, sc[1] = { (cuuint64_t)ldc * 2 };
 		cuuint32_t bc[2] = { STG_CHUNK_COLS, BM };
 		encode_map(&g->tmC, C, 2, dc, sc, bc, CU_TENSOR_MAP_SWIZZLE_64B);
 		if (ep.residual) encode_map(&g->tmR, ep.residual, 2, dc, sc, bc, CU_TENSOR_MAP_SWIZZLE_64B);
-	} else finish_setup(g, ep, m_tiles, sm_count);
+	} else {
+		if (ep.geglu) B200_FATAL("gemm_tc_prepare: GEGLU epilogue needs the persistent kernel (M=%lld N=%lld K=%lld)", (long long)M, (long long)N, (long long)K);
+		finish_setup(g, ep, m_tiles, sm_count);
+	}
 	cuuint64_t da[2] = { (cuuint64_t)K, (cuuint64_t)M }, sa[1] = { (cuuint64_t)lda * 2 };
 	cuuint32_t ba[2] = { BK, (cuuint32_t)(g->persistent ? p.a_rows : BM) };
 	encode_map(&g->tmA, A, 2, da, sa, ba);
@@ -823,6 +877,7 @@ static PersistentKernel persistent_variant(const GemmParams& p)
 {
 	const int act = p.act == U_NONE ? 0 : p.act == U_SILU ? 1 : 2;
 	const bool res = p.residual != nullptr;
+	if (p.geglu) return gemm_tc_persistent_kernel<3, false>;
 	switch (act * 2 + (res ? 1 : 0)) {
 	case 0: return gemm_tc_persistent_kernel<0, false>;
 	case 1: return gemm_tc_persistent_kernel<0, true>;
@@ -838,7 +893,7 @@ static void persistent_attrs_once()
 	if (done) return;
 	done = true;
 	PersistentKernel ks[] = { gemm_tc_persistent_kernel<0, false>, gemm_tc_persistent_kernel<0, true>, gemm_tc_persistent_kernel<1, false>,
-		gemm_tc_persistent_kernel<1, true>, gemm_tc_persistent_kernel<2, false>, gemm_tc_persistent_kernel<2, true> };
+		gemm_tc_persistent_kernel<1, true>, gemm_tc_persistent_kernel<2, false>, gemm_tc_persistent_kernel<2, true>, gemm_tc_persistent_kernel<3, false> };
 	for (PersistentKernel k : ks) CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 }
 

@@ -33,6 +33,11 @@ void k_im2col(cudaStream_t s, __half* col, int64_t kpad, const View& x, int KW, 
 // conv weight [KW,KH,Cin,Cout] (ggml order) -> [Cout][(kh*KW+kw)*Cin + c], row pitch kpad, f16.
 void k_conv_weight_prep(cudaStream_t s, __half* dst, int64_t kpad, const View& w);
 
+// GEGLU projection weights (mlblock_nn.c:159-172, rows [0,D) = value, [D,2D) = gate) re-ordered so that every group of 32
+// output columns holds 16 value columns followed by their 16 gate columns: the GEMM epilogue then gates in registers.
+// dst/src: 2D rows of `row_elems` elements (f16 weight rows, or row_elems = 1 for the f32 bias).
+void k_geglu_rows_prep(cudaStream_t s, void* dst, const View& src, int64_t D);
+
 // ---- attention (attention.cu)
 // o[d,q,h,b] = softmax_k(scale * q.k)[.] v ; q:[d,nq,H,B] k:[d,nk,H,B] v given as [nk,d,H,B] (ggml V^T view)
 void k_attention(cudaStream_t s, const View& o, const View& q, const View& k, const View& v, float scale, bool causal);
@@ -56,6 +61,7 @@ struct GemmEpilogue {
 	DT           residual_dt = DT_F16;
 	int64_t      ldr = 0;
 	UnaryOp      act = U_NONE;         // applied after bias/rowvec, before residual
+	bool         geglu = false;        // C[M, N/2]: out[:, 16j+i] = h[:, 32j+i] * gelu(h[:, 32j+16+i]) (weights/bias permuted by k_geglu_rows_prep)
 };
 
 struct GemmTC;  // opaque prepared launch (tensor maps etc.)

@@ -891,6 +891,29 @@ void k_geglu(cudaStream_t s, const View& dst, const View& h)
 	g_stats.kernel_launches++;
 }
 
+// ------------------------------------------------------------------ GEGLU weight / bias row permutation (once per weight version)
+__global__ void geglu_rows_prep_kernel(V4 dst, V4 src, long long D)
+{
+	const long long K = src.ne[0], total = 2 * D * K;
+	for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+		const long long r = e / K, k = e - r * K;
+		const long long blk = r >> 5, i = r & 31;
+		const long long sr = i < 16 ? blk * 16 + i : D + blk * 16 + (i - 16);
+		stv(dst, r * K + k, ldv(src, k * src.st[0] + sr * src.st[1]));
+	}
+}
+void k_geglu_rows_prep(cudaStream_t s, void* dst, const View& src, int64_t D)
+{
+	// src: [K, 2D] (weights) or [2D] viewed as [1, 2D] (bias)
+	View sv = src;
+	if (src.ne[1] == 1 && src.ne[0] == 2 * D) { sv.ne[0] = 1; sv.st[0] = 1; sv.ne[1] = 2 * D; sv.st[1] = src.st[0]; }
+	if (sv.ne[1] != 2 * D) B200_FATAL("k_geglu_rows_prep: expected %lld rows, got %lld", (long long)(2 * D), (long long)sv.ne[1]);
+	View dv = sv; dv.ptr = dst; dv.st[0] = 1; dv.st[1] = sv.ne[0];
+	long long total = 2 * D * sv.ne[0];
+	geglu_rows_prep_kernel<<<grid_for(total, 256, 2), 256, 0, s>>>(v4(dv), v4(sv), D);
+	g_stats.kernel_launches++;
+}
+
 // ------------------------------------------------------------------ im2col for strided / narrow convs
 __global__ void im2col_kernel(__half* __restrict__ col, long long kpad, V4 x, int KW, int KH,
 	int s0, int s1, int p0, int p1, int d0, int d1, long long OW, long long OH)

@@ -39,7 +39,7 @@ struct PT {                 // planned tensor: strided view over a buffer
 
 enum StepKind {
 	S_COPY, S_BINARY, S_UNARY, S_UPSCALE, S_SOFTMAX, S_GET_ROWS, S_TSEMB, S_GEMM_SIMT,
-	S_GROUPNORM, S_LAYERNORM, S_GEGLU, S_IM2COL, S_WPREP_CONV, S_ATTENTION, S_GEMM_TC, S_CONV_TC, S_ZERO, S_SOFTMAX_F16,
+	S_GROUPNORM, S_LAYERNORM, S_GEGLU, S_IM2COL, S_WPREP_CONV, S_ATTENTION, S_GEMM_TC, S_CONV_TC, S_ZERO, S_SOFTMAX_F16, S_WPREP_GEGLU,
 };
 
 struct Step {
@@ -333,6 +333,7 @@ struct Builder {
 	void plan();
 	void plan_one(ggml_tensor* t);
 	bool try_geglu(ggml_tensor* t);
+	bool match_geglu(const ggml_tensor* h, ggml_tensor** xv, ggml_tensor** gv, ggml_tensor** c, ggml_tensor** ge, ggml_tensor** mu);
 	void ensure_planned(const ggml_tensor* t);
 	void plan_node(ggml_tensor* t);
 	void plan_mul_mat(ggml_tensor* t);
@@ -506,6 +507,40 @@ void Builder::plan_mul_mat(ggml_tensor* t)
 		s.in[0] = A; s.in[1] = pa; s.n_in = 2;
 		s.M = rows; s.N = Mw; s.K = K; s.lda = pitch; s.ldb = pa.st[1]; s.ldc = Mw;
 		ggml_tensor* last = absorb_epilogue(t, s, 0, out);
+		// GEGLU projection (mlblock_nn.c:159-172): gate in the GEMM epilogue, half the columns ever reach memory
+		ggml_tensor *xv, *gv, *cg, *ge, *mu;
+		if (!env_flag("GGML_B200_NO_GEGLU_FUSION") && s.act == U_NONE && !s.has_residual && !s.has_rowvec && Mw % 64 == 0 &&
+			!(last->flags & GGML_TENSOR_FLAG_OUTPUT) && match_geglu(last, &xv, &gv, &cg, &ge, &mu)) {
+			const int64_t D = Mw / 2;
+			auto prep = [&](const ggml_tensor* leaf, const PT& src, DT dt, int64_t row_elems) {
+				auto it = prepared.find(leaf);
+				if (it != prepared.end()) return it->second;
+				int64_t ne[4] = { row_elems, Mw, 1, 1 };
+				PT wp = new_pt(dt, ne, BUF_PERSIST);
+				Step ps; ps.kind = S_WPREP_GEGLU; ps.name = "geglu_weight_prep"; ps.out = wp; ps.in[0] = src; ps.n_in = 1;
+				ps.iparam[0] = (int)D; ps.leaf = leaf;
+				P->prep.push_back(ps);
+				prepared[leaf] = wp;
+				return wp;
+			};
+			s.in[1] = prep(a, pa, DT_F16, K); s.ldb = K;
+			if (s.has_bias) {
+				const ggml_tensor* bl = nullptr;
+				for (ggml_tensor* u = t; u != last; ) { ggml_tensor* nx; single_user(u, &nx); if (nx->op == GGML_OP_ADD) bl = strip_reshape(nx->src[1]); u = nx; }
+				if (bl && bl->op == GGML_OP_NONE && s.bias.dt == DT_F32) s.bias = prep(bl, s.bias, DT_F32, 1);
+				else bl = nullptr;
+				if (!bl) B200_FATAL("GEGLU fusion: bias of '%s' is not a plain f32 parameter", t->name);
+			}
+			PT og; og.dt = DT_F16;
+			og.ne[0] = D; og.ne[1] = b->ne[1]; og.ne[2] = b->ne[2]; og.ne[3] = b->ne[3];
+			contiguous_strides(og);
+			og.buf = new_buf(BUF_ARENA, (size_t)og.numel() * 2);
+			s.out = og; s.ldc = D; s.iparam[0] = 1; s.name = "linear_geglu";
+			P->steps.push_back(s);
+			done[t] = done[last] = done[xv] = done[gv] = done[cg] = done[ge] = true;
+			finish(mu, og);
+			return;
+		}
 		// the [d, tokens] result of a linear may carry the residual in token-major layout too
 		s.out = out;
 		P->steps.push_back(s);
@@ -793,13 +828,13 @@ void Builder::plan_node(ggml_tensor* t)
 	}
 }
 
-// GEGLU gate (mlblock_nn.c:164-169): x,g = chunk(h); mul(x, gelu(cont(g))) -> one gate kernel.
-bool Builder::try_geglu(ggml_tensor* t)
+// GEGLU gate (mlblock_nn.c:164-169): x,g = chunk(h); mul(x, gelu(cont(g))).
+bool Builder::match_geglu(const ggml_tensor* h, ggml_tensor** pxv, ggml_tensor** pgv, ggml_tensor** pc, ggml_tensor** pge, ggml_tensor** pmu)
 {
-	if (t->op != GGML_OP_VIEW) return false;
-	const ggml_tensor* h = t->src[0];
-	auto& us = users[h];
-	if (!(us.size() == 2 && us[0]->op == GGML_OP_VIEW && us[1]->op == GGML_OP_VIEW && t == us[0] &&
+	auto it = users.find(h);
+	if (it == users.end()) return false;
+	auto& us = it->second;
+	if (!(us.size() == 2 && us[0]->op == GGML_OP_VIEW && us[1]->op == GGML_OP_VIEW &&
 		!(h->flags & GGML_TENSOR_FLAG_OUTPUT) && h->ne[0] % 16 == 0)) return false;
 	ggml_tensor *xv = us[0], *gv = us[1], *c, *ge, *mu;
 	size_t off0, off1; memcpy(&off0, xv->op_params, sizeof(off0)); memcpy(&off1, gv->op_params, sizeof(off1));
@@ -808,6 +843,17 @@ bool Builder::try_geglu(ggml_tensor* t)
 		single_user(gv, &c) && c->op == GGML_OP_CONT && single_user(c, &ge) && ge->op == GGML_OP_UNARY &&
 		ge->op_params[0] == GGML_UNARY_OP_GELU && single_user(ge, &mu) && mu->op == GGML_OP_MUL &&
 		mu->src[0] == xv && mu->src[1] == ge && users[xv].size() == 1)) return false;
+	*pxv = xv; *pgv = gv; *pc = c; *pge = ge; *pmu = mu;
+	return true;
+}
+
+// stand-alone gate kernel (when the projection did not absorb it)
+bool Builder::try_geglu(ggml_tensor* t)
+{
+	if (t->op != GGML_OP_VIEW) return false;
+	const ggml_tensor* h = t->src[0];
+	ggml_tensor *xv, *gv, *c, *ge, *mu;
+	if (!match_geglu(h, &xv, &gv, &c, &ge, &mu) || t != xv) return false;
 	PT ph = get(h);
 	if (!(ph.dt == DT_F16 && is_ggml_contig(ph))) return false;
 	PT o = new_pt(DT_F16, mu->ne);
@@ -950,6 +996,7 @@ static void run_step(Plan* P, Step& s, cudaStream_t st)
 		k_im2col(st, (__half*)buf_ptr(P, s.out), s.K, view_of(P, s.in[0]), s.iparam[0], s.iparam[1], s.iparam[2], s.iparam[3],
 			s.iparam[4], s.iparam[5], s.iparam[6], s.iparam[7], s.M, s.N);
 		break;
+	case S_WPREP_GEGLU: k_geglu_rows_prep(st, buf_ptr(P, s.out), view_of(P, s.in[0]), s.iparam[0]); break;
 	case S_WPREP_CONV: k_conv_weight_prep(st, (__half*)buf_ptr(P, s.out), s.iparam[0], view_of(P, s.in[0])); break;
 	case S_ATTENTION: {
 		View o = view_of(P, s.out), q = view_of(P, s.in[0]), k = view_of(P, s.in[1]), v = view_of(P, s.in[2]);
@@ -969,6 +1016,7 @@ static void run_step(Plan* P, Step& s, cudaStream_t st)
 			if (s.has_rowvec) { ep.rowvec = buf_ptr(P, s.rowvec); ep.rowvec_dt = s.rowvec.dt; ep.rowvec_stride = s.rowvec.ne[3] > 1 ? s.rowvec.st[3] : 0; ep.rows_per_image = s.rows_per_image; }
 			if (s.has_residual) { ep.residual = buf_ptr(P, s.residual); ep.residual_dt = s.residual.dt; ep.ldr = s.ldc; }
 			ep.act = s.act;
+			ep.geglu = s.kind == S_GEMM_TC && s.iparam[0] == 1;
 			if (s.kind == S_GEMM_TC)
 				s.tc = gemm_tc_prepare((const __half*)buf_ptr(P, s.in[0]), s.lda, (const __half*)buf_ptr(P, s.in[1]), s.ldb,
 					buf_ptr(P, s.out), s.out.dt, s.ldc, s.M, s.N, s.K, ep, P->be->sm_count);
@@ -984,7 +1032,7 @@ static void run_step(Plan* P, Step& s, cudaStream_t st)
 static void dump_plan(Plan* P)
 {
 	static const char* kn[] = { "COPY", "BINARY", "UNARY", "UPSCALE", "SOFTMAX", "GET_ROWS", "TSEMB", "GEMM_SIMT",
-		"GROUPNORM", "LAYERNORM", "GEGLU", "IM2COL", "WPREP_CONV", "ATTENTION", "GEMM_TC", "CONV_TC", "ZERO", "SOFTMAX_F16" };
+		"GROUPNORM", "LAYERNORM", "GEGLU", "IM2COL", "WPREP_CONV", "ATTENTION", "GEMM_TC", "CONV_TC", "ZERO", "SOFTMAX_F16", "WPREP_GEGLU" };
 	std::map<std::string, int> hist;
 	for (Step& s : P->steps) hist[kn[s.kind]]++;
 	std::string line;
