@@ -203,6 +203,8 @@ def main():
     # ---- warm-up (builds graphs, uploads weights, captures CUDA graphs)
     for i in range(max(args.warmup, 3)):
         imgs = gen(i, cached_cond=(i > 0))
+        if world > 1:
+            D.gather_arrays(np.stack(imgs), dst=0, device="cuda")     # also warms up the NCCL point-to-point channels
 
     # ---- `value`: device time of K generations, conditioning resident
     clocks = ClockSampler(local); clocks.start()
