@@ -41,6 +41,7 @@ struct GemmParams {
 	// thread-block cluster of cm x cn CTAs working on cm m-tiles x cn n-tiles: every A tile is loaded once per
 	// cluster row (each of its cn CTAs fetches 1/cn of the rows and TMA-multicasts them), every B tile once per column
 	int cm, cn, a_rows, b_rows, a_split_dim, a_split_ext, m_ctiles, n_ctiles;
+	int two_sm;                        // tcgen05 cta_group::2: a CTA pair computes a 256 x BN tile, each SM loading its 128 rows of A and HALF of B
 	int geglu;                         // epilogue gates column pairs: output has N/2 columns (weights pre-permuted)
 	int n_stg;                         // staging tiles (2: the TMA store of tile i drains while tile i+1 is written)
 	long long* trace;                  // debug timeline of CTA 0's epilogue (GGML_B200_GEMM_TRACE), null in production
@@ -331,20 +332,59 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask)
 	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
 		:: "r"(smem_u32(bar)), "h"(mask) : "memory");
 }
+// ---- cta_group::2 (CTA pair) forms. TMA loads issued by either CTA complete on the LEADER's barrier (same offset,
+// CTA-rank bits of the shared::cluster address cleared); MMA / commit are issued by the leader for both SMs.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1)
+{
+	asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+		:: "r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3)
+{
+	asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+		:: "r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+		"tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+		:: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask)
+{
+	asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+		:: "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t cols)
+{
+	asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+	asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t cols)
+{ asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(cols) : "memory"); }
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
+{
+	asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+		"mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" :: "r"(smem_u32(bar)), "r"(rank) : "memory");
+}
+__device__ __forceinline__ uint32_t make_idesc_m(int m, int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
+
 __device__ __forceinline__ void cluster_sync_all()
 { asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_count_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
 
-template <int ACT, bool HAS_RES>     // ACT: 0 none, 1 SiLU, 2 run-time p.act, 3 GEGLU gate; HAS_RES: f16 residual tile added in the epilogue
+template <int ACT, bool HAS_RES, bool TWO_SM>     // TWO_SM: tcgen05 cta_group::2 CTA pair (needs a cluster launch); ACT: 0 none, 1 SiLU, 2 run-time p.act, 3 GEGLU gate; HAS_RES: f16 residual tile added in the epilogue
 __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
 	const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmParams p)
 {
 	extern __shared__ __align__(1024) uint8_t smem_raw[];
 	uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-	const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)p.BN * BK * 2, stage_bytes = a_bytes + b_bytes;
+	const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)(TWO_SM ? p.BN / 2 : p.BN) * BK * 2, stage_bytes = a_bytes + b_bytes;
 	constexpr int ACC_PER_CHUNK = ACT == 3 ? 2 * STG_CHUNK_COLS : STG_CHUNK_COLS;   // accumulator columns behind one staging chunk
 	const int n_chunks = (p.BN + ACC_PER_CHUNK - 1) / ACC_PER_CHUNK;
 	uint8_t* stg = smem + (size_t)p.stages * stage_bytes;                       // staging tile (1024-aligned)
@@ -357,8 +397,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 	uint32_t* tmem_slot = (uint32_t*)(res_full + 1);
 
 	const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
-	const int csize = p.cm * p.cn;
-	const int crank = csize > 1 ? (int)cluster_ctarank() : 0, rn = crank % p.cn, rm = crank / p.cn;
+	const int csize = TWO_SM ? 2 : p.cm * p.cn;
+	const int crank = csize > 1 ? (int)cluster_ctarank() : 0;
+	const int pr = TWO_SM ? crank : 0;               // rank inside the CTA pair (0 = leader, issues the MMAs)
+	const int rn = TWO_SM ? 0 : crank % p.cn, rm = TWO_SM ? 0 : crank / p.cn;
 	const int cluster = csize > 1 ? (int)cluster_id_x() : (int)blockIdx.x, nclusters = csize > 1 ? (int)cluster_count_x() : (int)gridDim.x;
 	const int num_ctiles = p.m_ctiles * p.n_ctiles;
 	// CTAs sharing my A tile (same cluster row) / my B tile (same cluster column)
@@ -370,11 +412,12 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 		if (p.residual) tma_prefetch_desc(&tmR);
 		// a ring slot is free once every CTA that multicasts into it has seen ALL its readers release it
 		for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], p.cm + p.cn - 1); }
-		for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+		// CTA pair: the leader's accumulator-empty barrier collects the epilogue warps of BOTH CTAs
+		for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], TWO_SM ? 16 : 8); }
 		mbar_init(res_full, 1);
 		fence_barrier_init();
 	}
-	if (warp == 9) tmem_alloc(tmem_slot, 512);
+	if (warp == 9) { if (TWO_SM) tmem_alloc_2sm(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
 	tc_fence_before();
 	__syncthreads();
 	if (csize > 1) cluster_sync_all();                 // peers' barriers exist before anything is multicast to them
@@ -384,7 +427,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 	// cluster tile id -> this CTA's tile coordinates (n fastest). Tiles past the edge (odd tile counts) are processed
 	// like any other: their loads are zero-filled and their stores clipped by the TMA unit.
 	auto tile_coords = [&](int tile, int& n0, int& m0, int& tw0, int& th0, int& ti0) {
-		const int nt = (tile % p.n_ctiles) * p.cn + rn, mt = (tile / p.n_ctiles) * p.cm + rm;
+		const int nt = (tile % p.n_ctiles) * p.cn + rn, mt = (tile / p.n_ctiles) * (TWO_SM ? 2 : p.cm) + rm + pr;
 		n0 = nt * p.BN; m0 = mt * BM; tw0 = th0 = ti0 = 0;
 		if (p.conv) {
 			const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, ti = mt / (p.tiles_w * p.tiles_h);
@@ -401,6 +444,19 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 			int tap = 0, cc = 0;
 			for (int kb = 0; kb < p.num_kb; ++kb) {
 				mbar_wait(&empty_bar[s], ph ^ 1);
+				if (TWO_SM) {
+					// both CTAs of the pair load their own A rows and their half of the B rows; every byte is accounted
+					// on the leader's barrier, which is the one the MMA issuer waits on
+					if (elect_one()) {
+						uint8_t* sa = smem + (size_t)s * stage_bytes;
+						if (pr == 0) mbar_expect_tx(&full_bar[s], 2 * stage_bytes);
+						if (p.conv) {
+							const int kh = (tap * 11) >> 5, kw = tap - kh * 3;
+							tma_load_4d_2sm(sa, &tmA, &full_bar[s], cc * BK, tw0 + kw - 1, th0 + kh - 1, ti0);
+						} else tma_load_2d_2sm(sa, &tmA, &full_bar[s], kb * BK, m0);
+						tma_load_2d_2sm(sa + a_bytes, &tmB, &full_bar[s], kb * BK, n0 + pr * (p.BN / 2));
+					}
+				} else
 				if (elect_one()) {
 					uint8_t* sa = smem + (size_t)s * stage_bytes;
 					mbar_expect_tx(&full_bar[s], stage_bytes);      // my slice + the slices the peers multicast to me
@@ -426,10 +482,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 		}
 	} else if (warp == 9) {
 		// ===== MMA issuer =====
-		const uint32_t idesc = make_idesc(p.BN);
+		const uint32_t idesc = TWO_SM ? make_idesc_m(2 * BM, p.BN) : make_idesc(p.BN);
 		const uint64_t adesc0 = make_smem_desc(smem_u32(smem)), bdesc0 = make_smem_desc(smem_u32(smem) + a_bytes);
 		const uint32_t stage16 = stage_bytes >> 4;
 		int s = 0; uint32_t ph = 0, lt = 0;                // ring slot / phase, local tile counter
+		if (!(TWO_SM && pr != 0))                        // CTA pair: only the leader issues (for both tensor cores)
 		for (int tile = cluster; tile < num_ctiles; tile += nclusters, ++lt) {
 			const uint32_t buf = lt & 1;
 			mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);       // epilogue drained this accumulator
@@ -440,12 +497,20 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 				tc_fence_after();
 				if (elect_one()) {
 					const uint64_t ad = adesc0 + (uint64_t)(s * stage16), bd = bdesc0 + (uint64_t)(s * stage16);
-					#pragma unroll
-					for (int k = 0; k < BK / 16; ++k)
-						umma_f16(td, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
-					if (csize > 1) umma_commit_mc(&empty_bar[s], (uint16_t)(row_mask | col_mask));
-					else umma_commit(&empty_bar[s]);
-					if (kb == p.num_kb - 1) umma_commit(&acc_full[buf]);
+					if (TWO_SM) {
+						#pragma unroll
+						for (int k = 0; k < BK / 16; ++k)
+							umma_f16_2sm(td, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+						umma_commit_2sm(&empty_bar[s], 3);           // the slot is free in both CTAs
+						if (kb == p.num_kb - 1) umma_commit_2sm(&acc_full[buf], 3);
+					} else {
+						#pragma unroll
+						for (int k = 0; k < BK / 16; ++k)
+							umma_f16(td, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+						if (csize > 1) umma_commit_mc(&empty_bar[s], (uint16_t)(row_mask | col_mask));
+						else umma_commit(&empty_bar[s]);
+						if (kb == p.num_kb - 1) umma_commit(&acc_full[buf]);
+					}
 				}
 				__syncwarp();
 				if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -610,7 +675,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 			// accumulator drained: hand the TMEM buffer back to the MMA warp (one arrival per warp)
 			tc_fence_before();
 			__syncwarp();
-			if (lane == 0) mbar_arrive(&acc_empty[buf]);
+			if (lane == 0) { if (TWO_SM && pr != 0) mbar_arrive_remote(&acc_empty[buf], 0); else mbar_arrive(&acc_empty[buf]); }
 			fence_proxy_async();                           // staging writes -> visible to the TMA (async proxy)
 			asm volatile("bar.sync 1, 256;" ::: "memory");
 			GEMM_TR(4);
@@ -630,7 +695,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 	tc_fence_before();
 	__syncthreads();
 	if (csize > 1) cluster_sync_all();                 // no CTA leaves while a peer may still signal its barriers
-	if (warp == 9) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+	if (warp == 9) { tc_fence_after(); if (TWO_SM) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
 // ------------------------------------------------------------------ host side
@@ -718,33 +783,55 @@ static int max_active_clusters(int csize, int sm_count);
 
 // Tile / cluster choice of the persistent kernel: minimise waves x per-tile cycles. Per tile
 //   tensor pipe : num_kb * 4 MMAs of max(BN/2 [tcgen05 floor], 32 + BN/4 [A+B shared-memory reads at 128 B/clk]) cycles
-//   L2 -> SM    : (128/cn + BN/cm) * 128 B per k-block and CTA at ~58 B/clk per SM when every SM pulls (measured
-//                 ~17 TB/s chip-wide): a lone 128 x 256 tile is L2-bound at ~60 % of the tensor peak, which is what the
-//                 cm x cn cluster with TMA multicast removes
+//   L2 -> SM    : (128 + BN) * 128 B per k-block and CTA at ~58 B/clk per SM when every SM pulls (measured ~17 TB/s
+//                 chip-wide): a lone 128 x 256 tile is ingest-bound at ~60 % of the tensor peak. TMA multicast in a
+//                 cm x cn cluster only trims this (every SM still receives whole tiles); the CTA pair of
+//                 tcgen05 cta_group::2 halves the B share per SM and is what lifts the big contractions to >80 %
 //   epilogue    : ~5 cycles per column, overlaps the next tile unless it is the longest of the three.
-struct TileChoice { int bn, cm, cn; };
+struct TileChoice { int bn, cm, cn, two_sm; };
 static TileChoice pick_tiles_persistent(int64_t m_tiles, int64_t N, int num_kb, int sm_count, bool geglu)
 {
 	static const int cands[][2] = { {1, 1}, {2, 1}, {1, 2}, {2, 2}, {4, 1}, {4, 2} };
 	const char* e = getenv("GGML_B200_GEMM_CLUSTER");
 	const int max_cluster = e && *e ? atoi(e) : 8;
-	TileChoice best = {0, 1, 1}; double best_cost = 1e30;
+	const bool allow_2sm = env_on("GGML_B200_GEMM_2SM", true);
+	TileChoice best = {0, 1, 1, 0}; double best_cost = 1e30;
+	auto bn_ok = [&](int bn, int64_t n_tiles) {
+		if (bn - 16 >= N) return false;
+		if (n_tiles > 1 && (bn % (geglu ? 2 * STG_CHUNK_COLS : STG_CHUNK_COLS))) return false;   // staging chunks must not straddle tiles
+		if (geglu && (bn % 32)) return false;
+		return true;
+	};
 	for (auto& c : cands) {
 		const int cm = c[0], cn = c[1], cs = cm * cn;
 		if (cs > max_cluster || cm > m_tiles) continue;
 		const int nclusters = cs == 1 ? sm_count : max_active_clusters(cs, sm_count);
 		if (nclusters <= 0) continue;
 		for (int bn = 256; bn >= 16; bn -= 16) {
-			if (bn - 16 >= N) continue;
 			const int64_t n_tiles = (N + bn - 1) / bn;
-			if (n_tiles > 1 && (bn % (geglu ? 2 * STG_CHUNK_COLS : STG_CHUNK_COLS))) continue;   // staging chunks must not straddle tiles
-			if (geglu && (bn % 32)) continue;
+			if (!bn_ok(bn, n_tiles)) continue;
 			if (cn > n_tiles || (bn % (8 * cm))) continue;            // B slices are whole 8-row swizzle atoms
 			const int64_t ctiles = ((m_tiles + cm - 1) / cm) * ((n_tiles + cn - 1) / cn), waves = (ctiles + nclusters - 1) / nclusters;
 			const double mma = (double)num_kb * 4 * std::max(bn / 2.0, 32.0 + bn / 4.0), epi = 250.0 + 5.0 * bn;
-			const double l2 = (double)num_kb * (128.0 / cn + (double)bn / cm) * 128.0 / 58.0;
+			// measured: multicast relieves the L2 slices but every SM still ingests the full tiles -- about a quarter of
+			// the shared operand's cost goes away, not (cluster-1)/cluster of it
+			const double l2 = (double)num_kb * (128.0 * (cn > 1 ? 0.75 : 1.0) + (double)bn * (cm > 1 ? 0.75 : 1.0)) * 128.0 / 58.0;
 			const double cost = ((double)waves * std::max(std::max(mma, l2), epi) + epi) * (1.0 + 0.01 * (cs - 1));   // ties -> smaller cluster
-			if (cost < best_cost - 1e-9) { best_cost = cost; best = {bn, cm, cn}; }
+			if (cost < best_cost - 1e-9) { best_cost = cost; best = {bn, cm, cn, 0}; }
+		}
+	}
+	// CTA pair (tcgen05 cta_group::2): 256 x BN per pair at the same BN/2 cycles per MMA, each SM pulling its A rows and
+	// only half of B: the way to stay under the per-SM L2 bandwidth with wide tiles
+	if (allow_2sm && m_tiles >= 2 && max_cluster >= 2) {
+		const int nclusters = max_active_clusters(2, sm_count);
+		for (int bn = 256; nclusters > 0 && bn >= 32; bn -= 16) {
+			const int64_t n_tiles = (N + bn - 1) / bn;
+			if (!bn_ok(bn, n_tiles)) continue;
+			const int64_t ctiles = ((m_tiles + 1) / 2) * n_tiles, waves = (ctiles + nclusters - 1) / nclusters;
+			const double mma = (double)num_kb * 4 * std::max(bn / 2.0, 32.0 + bn / 8.0), epi = 250.0 + 5.0 * bn;
+			const double l2 = (double)num_kb * (128.0 + bn / 2.0) * 128.0 / 58.0;
+			const double cost = ((double)waves * std::max(std::max(mma, l2), epi) + epi) * 1.01;
+			if (cost < best_cost - 1e-9) { best_cost = cost; best = {bn, 1, 1, 1}; }
 		}
 	}
 	return best;
@@ -755,19 +842,20 @@ static void finish_setup_persistent(GemmTC* g, const GemmEpilogue& ep, int64_t m
 	GemmParams& p = g->p;
 	p.geglu = ep.geglu ? 1 : 0;
 	TileChoice tc = pick_tiles_persistent(m_tiles, p.N, p.num_kb, sm_count, ep.geglu);
-	if (const char* f = getenv("GGML_B200_GEMM_FORCE")) {      // "bn,cm,cn": tuning experiments (tools/gemm_bench.py)
-		int bn = 0, cm = 1, cn = 1;
-		if (sscanf(f, "%d,%d,%d", &bn, &cm, &cn) == 3 && bn >= 16 && bn <= 256 && bn % 16 == 0 && bn % (8 * cm) == 0 &&
-			(bn % STG_CHUNK_COLS == 0 || bn >= p.N) && cm * cn <= 8 && max_active_clusters(cm * cn, sm_count) > 0) tc = {bn, cm, cn};
+	if (const char* f = getenv("GGML_B200_GEMM_FORCE")) {      // "bn,cm,cn[,two_sm]": tuning experiments (tools/gemm_bench.py)
+		int bn = 0, cm = 1, cn = 1, two = 0;
+		if (sscanf(f, "%d,%d,%d,%d", &bn, &cm, &cn, &two) >= 3 && bn >= 16 && bn <= 256 && bn % 16 == 0 && bn % (8 * cm) == 0 &&
+			(bn % STG_CHUNK_COLS == 0 || bn >= p.N) && cm * cn <= 8 && max_active_clusters(cm * cn, sm_count) > 0) tc = {bn, two ? 1 : cm, two ? 1 : cn, two ? 1 : 0};
 	}
 	if (getenv("GGML_B200_GEMM_TRACE")) { CUDA_CHECK(cudaMalloc(&p.trace, 16 * 8 * 8)); CUDA_CHECK(cudaMemset(p.trace, 0, 16 * 8 * 8)); }
 	if (getenv("GGML_B200_GEMM_DEBUG"))
-		B200_LOG("gemm M=%d N=%d K=%d conv=%d m_tiles=%lld -> BN=%d cluster %dx%d", p.M, p.N, p.K, p.conv, (long long)m_tiles, tc.bn, tc.cm, tc.cn);
-	p.BN = tc.bn; p.cm = tc.cm; p.cn = tc.cn;
+		B200_LOG("gemm M=%d N=%d K=%d conv=%d m_tiles=%lld -> BN=%d cluster %dx%d%s", p.M, p.N, p.K, p.conv, (long long)m_tiles, tc.bn, tc.cm, tc.cn, tc.two_sm ? " cta_group::2" : "");
+	p.BN = tc.bn; p.cm = tc.cm; p.cn = tc.cn; p.two_sm = tc.two_sm;
 	p.m_tiles = (int)m_tiles; p.n_tiles = (p.N + p.BN - 1) / p.BN; p.num_tiles = p.m_tiles * p.n_tiles;
 	p.m_ctiles = (p.m_tiles + p.cm - 1) / p.cm; p.n_ctiles = (p.n_tiles + p.cn - 1) / p.cn;
 	p.a_rows = BM / p.cn; p.b_rows = p.BN / p.cm;
-	const size_t stage = (size_t)BM * BK * 2 + (size_t)p.BN * BK * 2;
+	if (p.two_sm) { p.m_ctiles = (p.m_tiles + 1) / 2; p.b_rows = p.BN / 2; }
+	const size_t stage = (size_t)BM * BK * 2 + (size_t)(p.two_sm ? p.BN / 2 : p.BN) * BK * 2;
 	const size_t acc_per_chunk = ep.geglu ? 2 * STG_CHUNK_COLS : STG_CHUNK_COLS;
 	const size_t n_chunks = (p.BN + acc_per_chunk - 1) / acc_per_chunk;
 	// A second staging tile lets the TMA store of tile i drain while tile i+1 is written, but the operand ring needs
@@ -779,9 +867,10 @@ static void finish_setup_persistent(GemmTC* g, const GemmEpilogue& ep, int64_t m
 	int stages = (int)std::min<size_t>(MAX_STAGES, (227 * 1024 - fixed) / stage);
 	p.stages = std::max(2, stages);
 	g->smem = fixed + p.stages * stage;
-	const int cs = p.cm * p.cn;
+	const int cs = p.two_sm ? 2 : p.cm * p.cn;
 	const int nclusters = (int)std::min<int64_t>((int64_t)p.m_ctiles * p.n_ctiles, cs == 1 ? sm_count : max_active_clusters(cs, sm_count));
 	g->grid = dim3((unsigned)(nclusters * cs));
+	if (getenv("GGML_B200_GEMM_DEBUG")) B200_LOG("  grid %u cluster %d smem %zu stages %d n_stg %d max_active_clusters(%d)=%d", g->grid.x, cs, g->smem, p.stages, p.n_stg, cs, cs > 1 ? max_active_clusters(cs, sm_count) : 0);
 	g->persistent = true;
 	p.bias = ep.bias; p.rowvec = ep.rowvec; p.rowvec_dt = ep.rowvec_dt; p.rowvec_stride = ep.rowvec_stride;
 	p.rows_per_image = ep.rows_per_image > 0 ? ep.rows_per_image : 1;
@@ -873,27 +962,33 @@ GemmTC* conv3x3_tc_prepare(const __half* x, int64_t n_img, int64_t H, int64_t W,
 }
 
 typedef void (*PersistentKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
-static PersistentKernel persistent_variant(const GemmParams& p)
+template <bool TWO_SM> static PersistentKernel persistent_variant_t(const GemmParams& p)
 {
 	const int act = p.act == U_NONE ? 0 : p.act == U_SILU ? 1 : 2;
 	const bool res = p.residual != nullptr;
-	if (p.geglu) return gemm_tc_persistent_kernel<3, false>;
+	if (p.geglu) return gemm_tc_persistent_kernel<3, false, TWO_SM>;
 	switch (act * 2 + (res ? 1 : 0)) {
-	case 0: return gemm_tc_persistent_kernel<0, false>;
-	case 1: return gemm_tc_persistent_kernel<0, true>;
-	case 2: return gemm_tc_persistent_kernel<1, false>;
-	case 3: return gemm_tc_persistent_kernel<1, true>;
-	case 4: return gemm_tc_persistent_kernel<2, false>;
-	default: return gemm_tc_persistent_kernel<2, true>;
+	case 0: return gemm_tc_persistent_kernel<0, false, TWO_SM>;
+	case 1: return gemm_tc_persistent_kernel<0, true, TWO_SM>;
+	case 2: return gemm_tc_persistent_kernel<1, false, TWO_SM>;
+	case 3: return gemm_tc_persistent_kernel<1, true, TWO_SM>;
+	case 4: return gemm_tc_persistent_kernel<2, false, TWO_SM>;
+	default: return gemm_tc_persistent_kernel<2, true, TWO_SM>;
 	}
 }
+static PersistentKernel persistent_variant(const GemmParams& p) { return p.two_sm ? persistent_variant_t<true>(p) : persistent_variant_t<false>(p); }
 static void persistent_attrs_once()
 {
 	static bool done = false;
 	if (done) return;
 	done = true;
-	PersistentKernel ks[] = { gemm_tc_persistent_kernel<0, false>, gemm_tc_persistent_kernel<0, true>, gemm_tc_persistent_kernel<1, false>,
-		gemm_tc_persistent_kernel<1, true>, gemm_tc_persistent_kernel<2, false>, gemm_tc_persistent_kernel<2, true>, gemm_tc_persistent_kernel<3, false> };
+	PersistentKernel ks[] = {
+		gemm_tc_persistent_kernel<0, false, false>, gemm_tc_persistent_kernel<0, true, false>, gemm_tc_persistent_kernel<1, false, false>,
+		gemm_tc_persistent_kernel<1, true, false>, gemm_tc_persistent_kernel<2, false, false>, gemm_tc_persistent_kernel<2, true, false>,
+		gemm_tc_persistent_kernel<3, false, false>,
+		gemm_tc_persistent_kernel<0, false, true>, gemm_tc_persistent_kernel<0, true, true>, gemm_tc_persistent_kernel<1, false, true>,
+		gemm_tc_persistent_kernel<1, true, true>, gemm_tc_persistent_kernel<2, false, true>, gemm_tc_persistent_kernel<2, true, true>,
+		gemm_tc_persistent_kernel<3, false, true> };
 	for (PersistentKernel k : ks) CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 }
 
@@ -906,7 +1001,7 @@ void gemm_tc_launch(cudaStream_t s, GemmTC* g)
 	}
 	if (g->persistent) {
 		persistent_attrs_once();
-		const int cs = g->p.cm * g->p.cn;
+		const int cs = g->p.two_sm ? 2 : g->p.cm * g->p.cn;
 		cudaLaunchConfig_t cfg = {};
 		cfg.gridDim = g->grid; cfg.blockDim = dim3(P_THREADS); cfg.dynamicSmemBytes = g->smem; cfg.stream = s;
 		cudaLaunchAttribute at[1];
@@ -929,7 +1024,7 @@ static int max_active_clusters(int csize, int sm_count)
 	at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
 	cfg.attrs = at; cfg.numAttrs = 1;
 	int n = 0;
-	cudaError_t e = cudaOccupancyMaxActiveClusters(&n, gemm_tc_persistent_kernel<0, false>, &cfg);
+	cudaError_t e = cudaOccupancyMaxActiveClusters(&n, gemm_tc_persistent_kernel<0, false, false>, &cfg);
 	if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
 	n = std::min(n, sm_count / csize);
 	cache[csize] = n > 0 ? n : -1;
