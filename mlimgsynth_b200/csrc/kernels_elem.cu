@@ -934,9 +934,35 @@ __global__ void im2col_kernel(__half* __restrict__ col, long long kpad, V4 x, in
 		col[e] = __float2half_rn(v);
 	}
 }
+// channels-last f16 input with Cin % 8 == 0: every (output pixel, tap) is a contiguous run of Cin channels -> 16-byte copies
+__global__ void im2col_vec_kernel(uint4* __restrict__ col, long long kpad8, const __half* __restrict__ x, long long W, long long H, long long C8,
+	long long sw, long long sh, long long sn, int KW, int KH, int s0, int s1, int p0, int p1, int d0, int d1, long long OW, long long OH, long long M)
+{
+	const long long K8 = (long long)KW * KH * C8, total = M * kpad8;
+	for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+		const long long m = e / kpad8, k = e - m * kpad8;
+		uint4 v = make_uint4(0u, 0u, 0u, 0u);
+		if (k < K8) {
+			const long long tap = k / C8, c8 = k - tap * C8; const int kw = (int)(tap % KW), kh = (int)(tap / KW);
+			const long long ow = m % OW, oh = (m / OW) % OH, n = m / (OW * OH);
+			const long long iw = ow * s0 + kw * d0 - p0, ih = oh * s1 + kh * d1 - p1;
+			if (iw >= 0 && iw < W && ih >= 0 && ih < H) v = __ldg(reinterpret_cast<const uint4*>(x + iw * sw + ih * sh + n * sn) + c8);
+		}
+		col[e] = v;
+	}
+}
+
 void k_im2col(cudaStream_t s, __half* col, int64_t kpad, const View& x, int KW, int KH,
 	int s0, int s1, int p0, int p1, int d0, int d1, int64_t OW, int64_t OH)
 {
+	if (x.dt == DT_F16 && x.st[2] == 1 && x.ne[2] % 8 == 0 && kpad % 8 == 0 && x.st[0] % 8 == 0 && x.st[1] % 8 == 0 && (x.ne[3] == 1 || x.st[3] % 8 == 0) &&
+		!((uintptr_t)x.ptr & 15) && !((uintptr_t)col & 15)) {
+		const long long M = OW * OH * x.ne[3], total = M * (kpad / 8);
+		im2col_vec_kernel<<<grid_for(total, 256, 2), 256, 0, s>>>((uint4*)col, kpad / 8, (const __half*)x.ptr, x.ne[0], x.ne[1], x.ne[2] / 8,
+			x.st[0], x.st[1], x.st[3], KW, KH, s0, s1, p0, p1, d0, d1, OW, OH, M);
+		g_stats.kernel_launches++;
+		return;
+	}
 	long long total = OW * OH * x.ne[3] * kpad;
 	im2col_kernel<<<grid_for(total, 256, 4), 256, 0, s>>>(col, kpad, v4(x), KW, KH, s0, s1, p0, p1, d0, d1, OW, OH);
 	g_stats.kernel_launches++;

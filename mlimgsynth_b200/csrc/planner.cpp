@@ -496,6 +496,55 @@ void Builder::plan_mul_mat(ggml_tensor* t)
 	bool weight2d = a->ne[2] == 1 && a->ne[3] == 1;
 	bool tc_ok = !force_simt && weight2d && pa.dt == DT_F16 && pa.st[0] == 1 && gemm_tc_supported(b->ne[1] * b->ne[2] * b->ne[3], Mw, K) &&
 		pa.st[1] % 8 == 0 && K % 8 == 0;
+	// Sibling projections of the same activation without bias / activation / residual (q, k, v of a self-attention,
+	// mlblock_nn.c:199-203; the k and v projections of the text context in every cross-attention, unet.c:110-145) run
+	// as ONE GEMM over the concatenated weight rows: the activation is streamed once instead of once per projection.
+	if (tc_ok && !env_flag("GGML_B200_NO_PROJ_FUSION")) {
+		auto plain = [&](const ggml_tensor* u) {
+			const ggml_tensor* w = u->src[0];
+			if (u->op != GGML_OP_MUL_MAT || u->src[1] != b || done.count(u) || (u->flags & GGML_TENSOR_FLAG_OUTPUT)) return false;
+			if (w->op != GGML_OP_NONE || w->type != GGML_TYPE_F16 || w->ne[0] != K || w->ne[2] != 1 || w->ne[3] != 1 || (w->nb[1] / 2) % 8) return false;
+			auto it = users.find(u);
+			if (it == users.end() || it->second.empty()) return false;
+			for (ggml_tensor* nx : it->second)
+				if (nx->op == GGML_OP_ADD || nx->op == GGML_OP_UNARY || nx->op == GGML_OP_MUL_MAT || nx->op == GGML_OP_SCALE) return false;   // has an epilogue / is an attention operand as-is
+			return true;
+		};
+		std::vector<ggml_tensor*> grp;
+		for (ggml_tensor* u : users[b]) if (plain(u) && std::find(grp.begin(), grp.end(), u) == grp.end()) grp.push_back(u);
+		if (grp.size() >= 2 && std::find(grp.begin(), grp.end(), t) != grp.end()) {
+			int64_t n_total = 0;
+			for (ggml_tensor* u : grp) n_total += u->src[0]->ne[1];
+			int64_t ne_w[4] = { K, n_total, 1, 1 };
+			PT wcat = new_pt(DT_F16, ne_w, BUF_PERSIST);
+			PT A = as_gemm_rows(pb);
+			int64_t rows, pitch; rows_uniform(A, rows, pitch);
+			PT out; out.dt = DT_F16;
+			out.ne[0] = n_total; out.ne[1] = b->ne[1]; out.ne[2] = b->ne[2]; out.ne[3] = b->ne[3];
+			contiguous_strides(out);
+			out.buf = new_buf(BUF_ARENA, (size_t)out.numel() * 2);
+			int64_t col = 0;
+			for (ggml_tensor* u : grp) {
+				const ggml_tensor* w = u->src[0];
+				PT sub = wcat; sub.ne[1] = w->ne[1]; sub.off = col * K;
+				Step ps; ps.kind = S_COPY; ps.name = "proj_weight_concat"; ps.out = sub; ps.in[0] = get(w); ps.n_in = 1; ps.leaf = w;
+				P->prep.push_back(ps);
+				col += w->ne[1];
+			}
+			Step s; s.kind = S_GEMM_TC; s.name = "linear_fused";
+			s.in[0] = A; s.in[1] = wcat; s.n_in = 2; s.out = out;
+			s.M = rows; s.N = n_total; s.K = K; s.lda = pitch; s.ldb = K; s.ldc = n_total;
+			P->steps.push_back(s);
+			col = 0;
+			for (ggml_tensor* u : grp) {
+				PT v = out; v.ne[0] = u->src[0]->ne[1]; v.off = col;
+				col += v.ne[0];
+				done[u] = true;
+				finish(u, v);
+			}
+			return;
+		}
+	}
 	if (tc_ok) {
 		PT A = as_gemm_rows(pb);
 		int64_t rows, pitch; rows_uniform(A, rows, pitch);
@@ -679,7 +728,10 @@ void Builder::plan_node(ggml_tensor* t)
 	} break;
 	case GGML_OP_CONT: {
 		PT a = get(t->src[0]);
-		if (is_dense(a)) finish(t, a);                         // a permutation of a compact buffer: no copy
+		// Every consumer works on strided views (and materialises one itself when it really needs contiguity), so an
+		// f16 view is passed through as it is: a permutation of a compact buffer, or a column slice of a fused
+		// projection (head split of q/k/v, mlblock_nn.c:204-222).
+		if (is_dense(a) || a.dt == DT_F16) finish(t, a);
 		else finish(t, to_contig(a, a.dt == DT_F32 ? DT_F16 : a.dt));
 	} break;
 	case GGML_OP_ADD: case GGML_OP_MUL: {
