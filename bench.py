@@ -31,6 +31,8 @@ WORKLOAD = "SD1.5 txt2img 512x512, 20 Euler steps, cfg 7, uniform schedule, rand
 N_STEPS_SAMPLER = 20
 FLOP_PER_NFE_SD15_512 = 0.803e12      # BASELINE.md section 2 (dense 2*MAC, conv + linear + attention)
 FLOP_VAE_512 = 2.515e12
+FLOP_PER_NFE_SDXL_1024 = 6.761e12
+SDXL_STEPS = 30
 
 
 def peaks():
@@ -146,6 +148,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sdxl", action="store_true", help="skip the SDXL 1024x1024 side measurement (second half of the BASELINE metric)")
+    ap.add_argument("--sdxl-batch", type=int, default=2, help="SDXL images per GPU per generation")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -264,12 +268,56 @@ def main():
         g_fl = prof.get("gemm_tc", {}).get("tflop", 0) + prof.get("conv3x3_tc", {}).get("tflop", 0)
         g_n = prof.get("gemm_tc", {}).get("launches", 0) + prof.get("conv3x3_tc", {}).get("launches", 0)
         achieved = g_fl / (g_ms / 1e3) if g_ms else 0.0
-        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM + implicit 3x3 conv)", "achieved": achieved, "peak": pk["bf16_tflops"],
+        roof = {"bound": "tensor", "kernel": "gemm_tc_persistent_kernel (tcgen05 cta_group::2 GEMM + implicit 3x3 conv; all linear / conv launches of one UNet evaluation)", "achieved": achieved, "peak": pk["bf16_tflops"],
                 "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"], "traffic": None, "peak_source": pk["src"],
                 "launches_per_unet_eval": g_n, "avg_launch_us": g_ms * 1e3 / g_n if g_n else None,
                 "unet_eval_ms_batch%d" % (2 * B): nfe_ms,
                 "unet_tflops": FLOP_PER_NFE_SD15_512 * 2 * B / (nfe_ms / 1e3) / 1e12,
                 "unet_frac_of_peak": FLOP_PER_NFE_SD15_512 * 2 * B / (nfe_ms / 1e3) / 1e12 / pk["bf16_tflops"]}
+
+    # ---- second half of the BASELINE metric: SDXL base 1024x1024, 30 Euler steps, cfg 7, full VAE decode
+    # (BASELINE configs[2] shape at --sdxl-batch images per GPU). Reported under config.sdxl_1024; the headline stays SD1.5.
+    sdxl = None
+    if not args.no_sdxl:
+        ctx.close(); ctx = None
+        if rank == 0:
+            weights_path("sdxl")
+        barrier()
+        xb = args.sdxl_batch
+        cx = api.Ctx(backend="B200:%d" % local, model=weights_path("sdxl"), image_dim=(1024, 1024), steps=SDXL_STEPS, method="euler", cfg_scale=7, batch_size=xb)
+        def genx(seed, cached):
+            cx.set("seed", D.image_seeds(seed * 1000, xb * world, rank, world)[0]); cx.set("prompt", PROMPT)
+            if cached:
+                cx.set("tensor_use_flags", api.TUF_CONDITIONING)
+            cx.generate()
+            return [cx.image(i) for i in range(xb)]
+        genx(0, False); genx(1, True)
+        barrier()
+        eng.ggml_b200_timer_start()
+        genx(2, True)
+        x_dev = allmax(eng.ggml_b200_timer_stop() / 1e3)
+        barrier()
+        t0 = time.perf_counter()
+        imgs = genx(3, False)
+        if world > 1:
+            D.gather_arrays(np.stack(imgs), dst=0, device="cuda")
+        barrier()
+        x_e2e = allmax(time.perf_counter() - t0)
+        if rank == 0:
+            lat = np.random.default_rng(0).standard_normal((2 * xb, 4, 128, 128)).astype(np.float32)
+            cond = (np.random.default_rng(1).standard_normal((2 * xb, 77, 2048)) * 0.5).astype(np.float32)
+            lab = (np.random.default_rng(2).standard_normal((2 * xb, 2816)) * 0.5).astype(np.float32)
+            cx.unet_eval(lat, cond, lab, 5.0); cx.unet_eval(lat, cond, lab, 5.0)
+            eng.ggml_b200_timer_start()
+            for _ in range(3):
+                cx.unet_eval(lat, cond, lab, 5.0)
+            x_nfe = eng.ggml_b200_timer_stop() / 3
+            tf = FLOP_PER_NFE_SDXL_1024 * 2 * xb / (x_nfe / 1e3) / 1e12
+            sdxl = {"workload": "SDXL base txt2img 1024x1024, %d Euler steps, cfg 7, full VAE decode, random-init weights" % SDXL_STEPS,
+                    "batch_per_gpu": xb, "images_per_sec": xb * world / x_dev, "e2e_images_per_sec": xb * world / x_e2e,
+                    "unet_it_per_s": SDXL_STEPS * xb * world / x_dev, "ms_per_generation": x_dev * 1e3,
+                    "unet_eval_ms_batch%d" % (2 * xb): x_nfe, "unet_tflops": tf, "unet_frac_of_peak": tf / peaks()["bf16_tflops"]}
+        cx.close()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -288,7 +336,8 @@ def main():
             "dtype": "f16 operands, f32 accumulate", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d (images), cfg halves batched" % world,
                        "unet_it_per_s": unet_it_s, "nfe_per_s": 2 * unet_it_s,
-                       "l2": "working set (weights 1.7 GB + activations) exceeds the 126 MB L2: every UNet evaluation streams all weights from HBM"},
+                       "l2": "working set (weights 1.7 GB + activations) exceeds the 126 MB L2: every UNet evaluation streams all weights from HBM",
+                       "sdxl_1024": sdxl},
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": (e1["h2d_bytes"] - e0["h2d_bytes"]) // args.steps,
                     "d2h_bytes_per_step": (e1["d2h_bytes"] - e0["d2h_bytes"]) // args.steps, "ms_per_step": e2e_s * 1e3 / args.steps},
             "gpu_launches": s1["kernel_launches"] - s0["kernel_launches"], "graph_replays": s1["graph_launches"] - s0["graph_launches"],
@@ -296,7 +345,8 @@ def main():
             "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "kernel_profile": prof,
         }
         print(json.dumps(line))
-    ctx.close()
+    if ctx is not None:
+        ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

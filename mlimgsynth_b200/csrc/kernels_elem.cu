@@ -822,8 +822,8 @@ static void layernorm_launch(cudaStream_t s, const void* x, void* y, long long r
 	bool vec = C % 8 == 0 && ldi % 8 == 0 && ldo % 8 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0 && C <= 2048;
 	if (!vec) { layernorm_scalar_kernel<TI, TO><<<grid, wpb * 32, 0, s>>>((const TI*)x, (TO*)y, rows, C, ldi, ldo, g, b, eps); return; }
 	if (sizeof(TI) == 2 && sizeof(TO) == 2 && C <= 256 * 5 && (!g || !((uintptr_t)g & 15)) && (!b || !((uintptr_t)b & 15))) {
-		// grid-stride fast path: 4 rows per warp at least, at most 16 blocks of 8 warps per SM
-		unsigned fg = (unsigned)std::min<long long>((rows + wpb * 4 - 1) / (wpb * 4), 148LL * 16);
+		// grid-stride fast path: one row per warp until the chip holds 16 blocks of 8 warps per SM, more rows per warp beyond
+		unsigned fg = (unsigned)std::min<long long>((rows + wpb - 1) / wpb, 148LL * 16);
 		fg = std::max(fg, 1u);
 		if (C <= 256) layernorm_fast_kernel<1><<<fg, wpb * 32, 0, s>>>((const __half*)x, (__half*)y, rows, C, ldi, ldo, g, b, eps);
 		else if (C <= 512) layernorm_fast_kernel<2><<<fg, wpb * 32, 0, s>>>((const __half*)x, (__half*)y, rows, C, ldi, ldo, g, b, eps);
