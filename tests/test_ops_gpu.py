@@ -247,3 +247,40 @@ def test_lora_merge_graph(ref, eng):
         t = g.ggml_scale_inplace(cc, t, 0.8)
         return g.ggml_add_inplace(cc, dst, t)
     check(build, ref, eng, OP_TOL)
+
+
+# ---------------------------------------------------------------- GEMM kernel variants
+# The tile / cluster / CTA-pair choice is made by a cost model at plan time; GGML_B200_GEMM_FORCE="bn,cm,cn,two_sm"
+# pins it so that every mode of the persistent kernel is checked on the same problems: 1-SM, TMA-multicast clusters
+# (cm x cn), and the tcgen05 cta_group::2 CTA pair, with tiles narrower and wider than N and odd tile counts.
+@pytest.mark.parametrize("force", ["64,1,1,1", "160,1,1,1", "256,1,1,1", "32,1,1,1", "128,2,1,0", "96,1,2,0", "64,2,2,0", "32,4,1,0", "48,1,1,0"])
+def test_gemm_modes(ref, eng, force, monkeypatch):
+    monkeypatch.setenv("GGML_B200_GEMM_FORCE", force)
+    check(lambda b: b.linear(b.inp(1000, 320), 320), ref, eng, OP_TOL)                       # odd tile count along M
+    check(lambda b: b.conv2d(b.inp(3, 128, 24, 40), 192), ref, eng, OP_TOL, seed=1)         # partial conv tiles, 3 images
+    def res_block(b):                                                                        # bias + time-embedding vector + SiLU + residual epilogues
+        return b.resnet(b.conv2d(b.inp(2, 4, 16, 16), 128), b.inp(2, 1280), 256)
+    check(res_block, ref, eng, BLOCK_TOL, seed=2)
+
+
+def test_geglu_fusion_matches_unfused(ref, eng, monkeypatch):
+    """The gate fused into the projection GEMM and the stand-alone gate kernel agree with the oracle and with each other."""
+    def build(b):
+        return b.feed_forward(b.inp(520, 320), 320)
+    (r,), (fused,) = run_both(build, ref, eng, 3)
+    monkeypatch.setenv("GGML_B200_NO_GEGLU_FUSION", "1")
+    (_,), (plain,) = run_both(build, ref, eng, 3)
+    assert max_rel_err(fused, r) <= BLOCK_TOL and max_rel_err(plain, r) <= BLOCK_TOL
+    assert max_rel_err(fused, plain) <= OP_TOL
+
+
+def test_projection_fusion_matches_unfused(ref, eng, monkeypatch):
+    """q/k/v run as one GEMM over concatenated weights (strided head views into attention) or as three."""
+    def build(b):
+        x = b.inp(1, 320, 16, 16); ctx = b.inp(77, 768)
+        return b.spatial_transf(x, ctx, 320, 8)
+    (r,), (fused,) = run_both(build, ref, eng, 4)
+    monkeypatch.setenv("GGML_B200_NO_PROJ_FUSION", "1")
+    (_,), (plain,) = run_both(build, ref, eng, 4)
+    assert max_rel_err(fused, r) <= BLOCK_TOL and max_rel_err(plain, r) <= BLOCK_TOL
+    assert max_rel_err(fused, plain) <= OP_TOL
