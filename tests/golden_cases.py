@@ -23,6 +23,16 @@ CASES = {
     "img2img_inpaint_lora": dict(opts=dict(method="euler", steps=5, cfg_scale=4, f_t_ini=0.7),
                                  cli=["-i", "@TMP@/in.ppm", "--imask", "@TMP@/mask.pgm", "--f-t-ini", "0.7", "-s", "5", "--method", "euler", "--cfg-scale", "4", "--lora", "@LORA@,0.8"]),
     "vae_tiled_decode": dict(cmd="vae-decode", cli=["--ilatent", "@TMP@/lat.tensor", "--vae-tile", "128"]),
+    # the other model families of BASELINE.json's configs (model = checkpoint kind of tools/gen_weights.py)
+    # config 2 shape: SD2.x v-prediction (unet.c:54,490-494), OpenCLIP ViT-H text encoder, d_head 64, DPM++(2M)
+    "sd2_vpred_dpmpp2m": dict(model="sd2", opts=dict(method="dpmpp2m", steps=4, cfg_scale=5, image_dim=(128, 192)),
+                              cli=["-d", "128,192", "-s", "4", "--method", "dpm++2m", "--cfg-scale", "5"]),
+    # config 3 shape: SDXL base (two text encoders, pooled-feature + size label, transformer depth 2 / 10)
+    "sdxl_euler_cfg": dict(model="sdxl", opts=dict(method="euler", steps=3, cfg_scale=7, image_dim=(192, 128)),
+                           cli=["-d", "192,128", "-s", "3", "--method", "euler", "--cfg-scale", "7"]),
+    # config 5: TAE decode instead of the VAE (tae.c:117)
+    "sd1_tae_decode": dict(model="sd1", tae=True, opts=dict(method="euler", steps=2, cfg_scale=3, image_dim=(128, 128)),
+                           cli=["-d", "128,128", "-s", "2", "--method", "euler", "--cfg-scale", "3", "--tae", "@TAE@"]),
 }
 
 

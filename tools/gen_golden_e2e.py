@@ -14,9 +14,11 @@ import golden_cases as G
 
 out_dir = os.path.join(ROOT, "tests", "golden", "e2e"); os.makedirs(out_dir, exist_ok=True)
 tmp = "/tmp/mlis_golden"; os.makedirs(tmp, exist_ok=True)
-model = os.path.join(tmp, "sd1.safetensors")
-if not os.path.exists(model):
-    gen_weights.write_safetensors(model, gen_weights.build_spec("sd1"), 1234, "f16")
+def weights(kind):
+    p = os.path.join(tmp, kind + ".safetensors")
+    if not os.path.exists(p):
+        gen_weights.write_safetensors(p, gen_weights.build_spec(kind), 1234, "f16")
+    return p
 lora = os.path.join(tmp, "lora1.safetensors")
 gen_weights.write_lora(lora, "sd1", rank=8, alpha=8.0, seed=5)
 G.write_inputs(tmp)
@@ -26,7 +28,9 @@ for name, case in G.CASES.items():
     if os.path.exists(dst) and "--force" not in sys.argv:
         continue
     o = os.path.join(tmp, name)
-    cli = [a.replace("@TMP@", tmp).replace("@LORA@", lora) for a in case["cli"]]
+    model = weights(case.get("model", "sd1"))
+    tae = weights("tae") if case.get("tae") else ""
+    cli = [a.replace("@TMP@", tmp).replace("@LORA@", lora).replace("@TAE@", tae) for a in case["cli"]]
     if case.get("cmd") == "vae-decode":
         cmd = [exe, "vae-decode", "-m", model, "-o", o + ".pnm"] + cli
     else:

@@ -261,7 +261,10 @@ def spec_tae(S):
         i += 1                  # upsample
         S.conv(p + "%d" % i, c, c, 3, bias=False); i += 1
     tae_block(S, p + "%d." % i, c); i += 1
-    S.conv(p + "%d" % i, c, 3, 3)
+    # the decoder emits the image in [0,1] directly (tae.c:65-92): centre the random-init output at mid-grey so that
+    # the parity fixtures are not clamped to black
+    S.add(p + "%d.weight" % i, (3, c, 3, 3), "w")
+    S.add(p + "%d.bias" % i, (3,), "b_mid")
     p = "encoder.layers."
     S.conv(p + "0", 3, c, 3)
     tae_block(S, p + "1.", c)
@@ -301,6 +304,8 @@ def gen_tensor(name, shape, kind, seed):
         x *= GAIN / np.sqrt(fan_in)
     elif kind == "b":
         x *= 0.02
+    elif kind == "b_mid":
+        x = 0.5 + 0.02 * x
     elif kind == "nw":
         x = 1.0 + 0.05 * x
     elif kind == "nb":
