@@ -45,7 +45,12 @@ struct GemmParams {
 	int geglu;                         // epilogue gates column pairs: output has N/2 columns (weights pre-permuted)
 	int n_stg;                         // staging tiles (2: the TMA store of tile i drains while tile i+1 is written)
 	long long* trace;                  // debug timeline of CTA 0's epilogue (GGML_B200_GEMM_TRACE), null in production
+	uint32_t mul_nct, mul_tw, mul_th;  // reciprocal multipliers of n_ctiles / tiles_w / tiles_h: tile coordinates without integer division
 };
+
+// q = n / d through one multiply-high: mul = ceil(2^32 / d) is exact while n * d < 2^32 (tile counts are far below); d == 1 has mul == 0
+static uint32_t fastdiv_mul(uint32_t d) { return d <= 1 ? 0u : (uint32_t)((0x100000000ull + d - 1) / d); }
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, uint32_t mul) { return mul ? __umulhi(n, mul) : n; }
 
 struct GemmTC {
 	CUtensorMap tmA, tmB, tmC, tmR;     // tmC / tmR: output store / residual load maps of the persistent kernel
@@ -82,6 +87,16 @@ __device__ __forceinline__ float gelu_tanh_fast(float g)
 	const float u = 0.79788456080286535588f * g * fmaf(0.044715f * g, g, 1.0f);
 	float t; asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
 	return 0.5f * g * (1.0f + t);
+}
+
+// (x + b) * gelu_tanh(g) with xb_half = b / 2: 7 FMA-pipe operations + one MUFU.TANH per output
+//   gelu(g) = g/2 * (1 + tanh(g * (k0 + k1 g^2))),  k0 = sqrt(2/pi), k1 = 0.044715 k0
+__device__ __forceinline__ float geglu_gate(float x, float xb_half, float g)
+{
+	const float t = fmaf(g * g, 0.79788456080286535588f * 0.044715f, 0.79788456080286535588f);
+	float th; asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(g * t));
+	const float w = fmaf(x, 0.5f, xb_half) * g;
+	return fmaf(w, th, w);
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -363,11 +378,13 @@ __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t cols
 }
 __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t cols)
 { asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(cols) : "memory"); }
-// arrive on the barrier at the same offset in CTA `rank` of the cluster
+// arrive on the barrier at the same offset in CTA `rank` of the cluster. No .release.cluster qualifier: that form costs a
+// GPU-scope memory barrier (MEMBAR.ALL.GPU + ERRBAR) per arrival, and what the arrival orders here are tensor-memory
+// reads that tcgen05.wait::ld + tcgen05.fence::before_thread_sync have already completed.
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
 {
 	asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
-		"mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" :: "r"(smem_u32(bar)), "r"(rank) : "memory");
+		"mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" :: "r"(smem_u32(bar)), "r"(rank) : "memory");
 }
 __device__ __forceinline__ uint32_t make_idesc_m(int m, int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
 
@@ -427,11 +444,12 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 	// cluster tile id -> this CTA's tile coordinates (n fastest). Tiles past the edge (odd tile counts) are processed
 	// like any other: their loads are zero-filled and their stores clipped by the TMA unit.
 	auto tile_coords = [&](int tile, int& n0, int& m0, int& tw0, int& th0, int& ti0) {
-		const int nt = (tile % p.n_ctiles) * p.cn + rn, mt = (tile / p.n_ctiles) * (TWO_SM ? 2 : p.cm) + rm + pr;
+		const int mq = (int)fastdiv((uint32_t)tile, p.mul_nct);                  // tile / n_ctiles
+		const int nt = (tile - mq * p.n_ctiles) * p.cn + rn, mt = mq * (TWO_SM ? 2 : p.cm) + rm + pr;
 		n0 = nt * p.BN; m0 = mt * BM; tw0 = th0 = ti0 = 0;
 		if (p.conv) {
-			const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, ti = mt / (p.tiles_w * p.tiles_h);
-			tw0 = tw * p.bw; th0 = th * p.bh; ti0 = ti * p.bi;
+			const int q1 = (int)fastdiv((uint32_t)mt, p.mul_tw), ti = (int)fastdiv((uint32_t)q1, p.mul_th);   // mt / tiles_w, / tiles_h
+			tw0 = (mt - q1 * p.tiles_w) * p.bw; th0 = (q1 - ti * p.tiles_h) * p.bh; ti0 = ti * p.bi;
 		}
 	};
 
@@ -535,7 +553,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 		const bool chunk_owner = lane == 0 && warp < n_chunks;    // lane 0 of warp w stores (and re-fills) staging chunk w
 		uint8_t* my_chunk0 = stg + warp * STG_CHUNK_BYTES;
 		auto bias_of = [&](int e, int n0, int ti0) {       // bias + per-image vector of staged element e
-			const int im_l = e / p.BN, c = e - im_l * p.BN, col = n0 + c;
+			const int im_l = n_img_tile > 1 ? e / p.BN : 0, c = e - im_l * p.BN, col = n0 + c;
 			float v = 0.f;
 			if (col < p.N) {
 				if (p.bias) v = __ldg(p.bias + col);
@@ -545,6 +563,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 					v += p.rowvec_dt == DT_F16 ? __half2float(((const __half*)p.rowvec)[o]) : ((const float*)p.rowvec)[o];
 				}
 			}
+			if (ACT == 3 && !(c & 16)) v *= 0.5f;          // GEGLU value columns: the gate's factor 1/2 is folded into value and bias
 			return v;
 		};
 		auto res_load = [&](int tile, uint32_t sbuf) {     // chunk owners: residual chunk of `tile` -> staging tile sbuf
@@ -625,12 +644,12 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 				float f[16];
 				#pragma unroll
 				for (int j = 0; j < 16; j += 4) {
-					float4 bx = make_float4(0.f, 0.f, 0.f, 0.f), bg = bx;
+					float4 bx = make_float4(0.f, 0.f, 0.f, 0.f), bg = bx;        // bx holds HALF the value bias (bias_of)
 					if (has_vec) { bx = lds128f(my_vec + (c0 + j) * 4); bg = lds128f(my_vec + (c0 + 16 + j) * 4); }
-					f[j]     = (__uint_as_float(vx[j])     + bx.x) * gelu_tanh_fast(__uint_as_float(vg[j])     + bg.x);
-					f[j + 1] = (__uint_as_float(vx[j + 1]) + bx.y) * gelu_tanh_fast(__uint_as_float(vg[j + 1]) + bg.y);
-					f[j + 2] = (__uint_as_float(vx[j + 2]) + bx.z) * gelu_tanh_fast(__uint_as_float(vg[j + 2]) + bg.z);
-					f[j + 3] = (__uint_as_float(vx[j + 3]) + bx.w) * gelu_tanh_fast(__uint_as_float(vg[j + 3]) + bg.w);
+					f[j]     = geglu_gate(__uint_as_float(vx[j]),     bx.x, __uint_as_float(vg[j])     + bg.x);
+					f[j + 1] = geglu_gate(__uint_as_float(vx[j + 1]), bx.y, __uint_as_float(vg[j + 1]) + bg.y);
+					f[j + 2] = geglu_gate(__uint_as_float(vx[j + 2]), bx.z, __uint_as_float(vg[j + 2]) + bg.z);
+					f[j + 3] = geglu_gate(__uint_as_float(vx[j + 3]), bx.w, __uint_as_float(vg[j + 3]) + bg.w);
 				}
 				const int oc = c0 >> 1;                            // output column inside the tile
 				const uint32_t chunk = my_row + (uint32_t)(oc / STG_CHUNK_COLS) * STG_CHUNK_BYTES;
@@ -855,6 +874,7 @@ static void finish_setup_persistent(GemmTC* g, const GemmEpilogue& ep, int64_t m
 	p.m_ctiles = (p.m_tiles + p.cm - 1) / p.cm; p.n_ctiles = (p.n_tiles + p.cn - 1) / p.cn;
 	p.a_rows = BM / p.cn; p.b_rows = p.BN / p.cm;
 	if (p.two_sm) { p.m_ctiles = (p.m_tiles + 1) / 2; p.b_rows = p.BN / 2; }
+	p.mul_nct = fastdiv_mul((uint32_t)p.n_ctiles); p.mul_tw = fastdiv_mul((uint32_t)std::max(1, p.tiles_w)); p.mul_th = fastdiv_mul((uint32_t)std::max(1, p.tiles_h));
 	const size_t stage = (size_t)BM * BK * 2 + (size_t)(p.two_sm ? p.BN / 2 : p.BN) * BK * 2;
 	const size_t acc_per_chunk = ep.geglu ? 2 * STG_CHUNK_COLS : STG_CHUNK_COLS;
 	const size_t n_chunks = (p.BN + acc_per_chunk - 1) / acc_per_chunk;
@@ -862,7 +882,11 @@ static void finish_setup_persistent(GemmTC* g, const GemmEpilogue& ep, int64_t m
 	// ~150 KB in flight to cover the ~2500-cycle loaded L2 latency at 57 B/clk: only take it when 5 stages still fit.
 	p.n_stg = 1;
 	auto fixed_bytes = [&](int n_stg) { return 1024 + n_stg * n_chunks * STG_CHUNK_BYTES + (size_t)P_EPI_MAX_IMG * 256 * 4 + (2 * MAX_STAGES + 5) * 8 + 64; };
-	if ((227 * 1024 - fixed_bytes(2)) / stage >= 5) p.n_stg = 2;
+	// GEGLU tiles are epilogue-bound when K is short (the gate costs ~10 cycles per column): there the second staging tile
+	// is worth a ring stage
+	const int min_stages_2stg = (ep.geglu && p.num_kb <= 8) ? 4 : 5;
+	if ((227 * 1024 - fixed_bytes(2)) / stage >= (size_t)min_stages_2stg) p.n_stg = 2;
+	if (const char* e = getenv("GGML_B200_GEMM_NSTG")) { const int v = atoi(e); if ((v == 1 || v == 2) && (227 * 1024 - fixed_bytes(v)) / stage >= 2) p.n_stg = v; }
 	const size_t fixed = fixed_bytes(p.n_stg);
 	int stages = (int)std::min<size_t>(MAX_STAGES, (227 * 1024 - fixed) / stage);
 	p.stages = std::max(2, stages);

@@ -3,6 +3,7 @@
 // Rooflines: everything in this file is HBM/L2-bandwidth bound; the hot ones are vectorised
 // to 16-byte accesses with channels innermost so that a warp touches contiguous 512 B.
 #include "kernels.h"
+#include "tc_common.cuh"
 #include <algorithm>
 
 namespace b200 {
@@ -505,7 +506,10 @@ __device__ __forceinline__ uint4 f_to_h8(const float* v)
 	return raw;
 }
 
-__global__ void gn_stats_fast_kernel(const __half* __restrict__ x, long long HW, int C, int cpg, int groups,
+constexpr int GN_BLOCKS_PER_SM = 5;      // both fast kernels are compiled for 5 resident blocks of <= 256 threads per SM (48 registers)
+
+__global__ void __launch_bounds__(256, GN_BLOCKS_PER_SM)
+gn_stats_fast_kernel(const __half* __restrict__ x, long long HW, int C, int cpg, int groups,
 	long long img_stride, long long pix_stride, double* __restrict__ stats, int pix_per_block, int slab_chunks, int nslabs)
 {
 	extern __shared__ float sm[];  // [groups][2]
@@ -552,28 +556,42 @@ __global__ void gn_stats_fast_kernel(const __half* __restrict__ x, long long HW,
 		if (sm[i] != 0.f) atomicAdd(&stats[(long long)n * groups * 2 + i], (double)sm[i]);
 }
 
+// x * sigmoid(x) = x * (0.5 + 0.5 tanh(x / 2)): one MUFU op per element (tanh.approx) instead of ex2 + rcp
+__device__ __forceinline__ float silu_tanh(float t)
+{
+	float th; asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * t));
+	const float h = 0.5f * t;
+	return fmaf(h, th, h);
+}
+
 template <bool SILU>
-__global__ void gn_apply_fast_kernel(const __half* __restrict__ x, __half* __restrict__ y, long long HW, int C, int cpg, int groups,
+__global__ void __launch_bounds__(256, GN_BLOCKS_PER_SM)
+gn_apply_fast_kernel(const __half* __restrict__ x, __half* __restrict__ y, long long HW, int C, int cpg, int groups,
 	long long img_stride, long long pix_stride, long long oimg_stride, long long opix_stride,
 	const float* __restrict__ gamma, const float* __restrict__ beta, const double* __restrict__ stats,
 	float eps, int pix_per_block, int slab_chunks, int nslabs)
 {
+	extern __shared__ float sm[];  // mean[groups], rstd[groups]: the double-precision finish runs once per group and block
 	const int n = blockIdx.y;
 	const int tile = blockIdx.x / nslabs, slab = blockIdx.x - tile * nslabs;
+	const double cnt = (double)HW * cpg;
+	for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+		const double su = stats[((long long)n * groups + g) * 2], sq = stats[((long long)n * groups + g) * 2 + 1];
+		const double mean = su / cnt; double var = sq / cnt - mean * mean; if (var < 0) var = 0;
+		sm[g] = (float)mean;
+		sm[groups + g] = (float)(1.0 / sqrt(var + (double)eps));
+	}
+	__syncthreads();
 	const int chunks = C / 8;
 	const int ch = slab * slab_chunks + (int)(threadIdx.x % slab_chunks);
 	const int plane = threadIdx.x / slab_chunks, planes = blockDim.x / slab_chunks;
 	if (ch >= chunks) return;
-	const double cnt = (double)HW * cpg;
 	float sc[8], sh[8];
 	#pragma unroll
 	for (int j = 0; j < 8; ++j) {
 		const int c = ch * 8 + j, g = c / cpg;
-		const double su = stats[((long long)n * groups + g) * 2], sq = stats[((long long)n * groups + g) * 2 + 1];
-		const double mean = su / cnt; double var = sq / cnt - mean * mean; if (var < 0) var = 0;
-		const float rstd = (float)(1.0 / sqrt(var + (double)eps));
 		const float ga = gamma ? gamma[c] : 1.f, be = (gamma && beta) ? beta[c] : 0.f;
-		sc[j] = rstd * ga; sh[j] = be - (float)mean * rstd * ga;
+		sc[j] = sm[groups + g] * ga; sh[j] = be - sm[g] * sc[j];
 	}
 	const long long p0 = (long long)tile * pix_per_block, p1 = min(HW, p0 + pix_per_block);
 	const __half* base = x + n * img_stride + ch * 8;
@@ -581,7 +599,7 @@ __global__ void gn_apply_fast_kernel(const __half* __restrict__ x, __half* __res
 	auto apply = [&](const uint4& raw) {
 		float v[8]; h8_to_f(raw, v);
 		#pragma unroll
-		for (int j = 0; j < 8; ++j) { float t = fmaf(v[j], sc[j], sh[j]); if (SILU) t = __fdividef(t, 1.0f + __expf(-t)); v[j] = t; }
+		for (int j = 0; j < 8; ++j) { float t = fmaf(v[j], sc[j], sh[j]); if (SILU) t = silu_tanh(t); v[j] = t; }
 		return f_to_h8(v);
 	};
 	long long p = p0 + plane;
@@ -608,18 +626,21 @@ void k_groupnorm(cudaStream_t s, const View& dst, const View& src, const float* 
 		const int chunks = C / 8;
 		const int nslabs = (chunks + 255) / 256, slab_chunks = (chunks + nslabs - 1) / nslabs;
 		const int planes = std::max(1, 256 / slab_chunks), threads = slab_chunks * planes;
-		// pixels per block: 16 per thread, fewer for small tensors so that the grid still covers the chip twice
-		int ppt = 16;
-		while (ppt > 2 && ((HW + (long long)planes * ppt - 1) / ((long long)planes * ppt)) * N * nslabs < 148LL * 4) ppt /= 2;
-		const int pix_per_block = planes * ppt;
+		// One exact wave: 148 SMs x GN_BLOCKS_PER_SM resident blocks share the pixels evenly (no tail wave, every SM equally
+		// loaded); small tensors get one pixel row of `planes` pixels per block at least.
+		const long long target = 148LL * GN_BLOCKS_PER_SM;
+		const long long tiles_want = std::max<long long>(1, target / std::max<long long>(1, N * nslabs));
+		long long ppb = (HW + tiles_want - 1) / tiles_want;
+		ppb = std::max<long long>(planes, (ppb + planes - 1) / planes * planes);
+		const int pix_per_block = (int)std::min<long long>(ppb, 1 << 30);
 		dim3 grid((unsigned)(((HW + pix_per_block - 1) / pix_per_block) * nslabs), (unsigned)N);
 		const size_t smem = groups * 2 * sizeof(float);
 		gn_stats_fast_kernel<<<grid, threads, smem, s>>>((const __half*)src.ptr, HW, C, cpg, groups, src.st[3], src.st[0], stats, pix_per_block, slab_chunks, nslabs);
 		if (silu)
-			gn_apply_fast_kernel<true><<<grid, threads, 0, s>>>((const __half*)src.ptr, (__half*)dst.ptr, HW, C, cpg, groups, src.st[3], src.st[0],
+			gn_apply_fast_kernel<true><<<grid, threads, smem, s>>>((const __half*)src.ptr, (__half*)dst.ptr, HW, C, cpg, groups, src.st[3], src.st[0],
 				dst.st[3], dst.st[0], gamma, beta, stats, eps, pix_per_block, slab_chunks, nslabs);
 		else
-			gn_apply_fast_kernel<false><<<grid, threads, 0, s>>>((const __half*)src.ptr, (__half*)dst.ptr, HW, C, cpg, groups, src.st[3], src.st[0],
+			gn_apply_fast_kernel<false><<<grid, threads, smem, s>>>((const __half*)src.ptr, (__half*)dst.ptr, HW, C, cpg, groups, src.st[3], src.st[0],
 				dst.st[3], dst.st[0], gamma, beta, stats, eps, pix_per_block, slab_chunks, nslabs);
 		g_stats.kernel_launches += 2;
 		return;
@@ -718,19 +739,33 @@ __global__ void layernorm_kernel(const TI* __restrict__ x, TO* __restrict__ y, l
 	}
 }
 
-// ---- fast path (f16 -> f16): a warp walks rows with a grid stride; gamma / beta live in registers for the whole
-// kernel (vector loads, once), and the next row is already in flight while the current one is reduced and stored.
-template <int NCH>
-__global__ void layernorm_fast_kernel(const __half* __restrict__ x, __half* __restrict__ y, long long rows, int C,
+// ---- fast path (f16 -> f16): persistent grid (exactly the resident blocks of the chip). A row is owned by LPR lanes
+// (LPR * NCH 8-element chunks, chunk = lane_in_row + i * LPR), so a warp works on 32 / LPR rows at once with every lane
+// busy: the row widths of the diffusion models are 320 * 2^k = 40 * 2^k chunks, which a lane-per-chunk mapping would
+// leave 37 % idle. gamma / beta of the lane's chunks live in registers for the whole kernel; the next row group is in
+// flight while the current one is reduced (two exact passes, f32, butterfly over the LPR lanes) and stored.
+template <int LPR, int NCH>
+__global__ void __launch_bounds__(256)
+layernorm_fast_kernel(const __half* __restrict__ x, __half* __restrict__ y, long long rows, int C,
 	long long ld_in, long long ld_out, const float* __restrict__ gamma, const float* __restrict__ beta, float eps)
 {
+	constexpr int RW = 32 / LPR;                        // rows per warp and iteration
 	const int lane = threadIdx.x & 31, chunks = C >> 3;
-	const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
-	long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+	const int li = lane % LPR, sub = lane / LPR;
+	const long long wstride = (long long)gridDim.x * (blockDim.x >> 5) * RW;
+	long long row = (blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5)) * RW + sub;
+	uint4 cur[NCH], nxt[NCH];
+	auto load = [&](long long r, uint4* dst) {
+		if (r < rows) {
+			#pragma unroll
+			for (int i = 0; i < NCH; ++i) { const int ch = li + i * LPR; if (ch < chunks) dst[i] = *reinterpret_cast<const uint4*>(x + r * ld_in + ch * 8); }
+		}
+	};
+	load(row, cur);
 	float ga[NCH][8], be[NCH][8];
 	#pragma unroll
 	for (int i = 0; i < NCH; ++i) {
-		const int ch = lane + i * 32;
+		const int ch = li + i * LPR;
 		#pragma unroll
 		for (int j = 0; j < 8; ++j) { ga[i][j] = 1.f; be[i][j] = 0.f; }
 		if (ch < chunks && gamma) {
@@ -742,50 +777,87 @@ __global__ void layernorm_fast_kernel(const __half* __restrict__ x, __half* __re
 			}
 		}
 	}
-	uint4 cur[NCH], nxt[NCH];
-	auto load = [&](long long r, uint4* dst) {
-		#pragma unroll
-		for (int i = 0; i < NCH; ++i) { const int ch = lane + i * 32; if (ch < chunks) dst[i] = *reinterpret_cast<const uint4*>(x + r * ld_in + ch * 8); }
-	};
-	if (row < rows) load(row, cur);
 	const float inv_c = 1.0f / C;
-	for (; row < rows; row += wstride) {
-		const long long nrow = row + wstride;
-		if (nrow < rows) load(nrow, nxt);
+	// every lane of the warp runs the same number of iterations (the shuffles need all of them): loop on the group base
+	for (long long base = row - sub; base < rows; base += wstride, row += wstride) {
+		load(row + wstride, nxt);
 		float v[NCH][8];
 		float sum = 0.f;
 		#pragma unroll
 		for (int i = 0; i < NCH; ++i) {
-			if (lane + i * 32 < chunks) { h8_to_f(cur[i], v[i]);
+			if (li + i * LPR < chunks && row < rows) { h8_to_f(cur[i], v[i]);
 				#pragma unroll
 				for (int j = 0; j < 8; ++j) sum += v[i][j]; }
+			else {
+				#pragma unroll
+				for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+			}
 		}
 		#pragma unroll
-		for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(~0u, sum, o);
+		for (int o = LPR / 2; o; o >>= 1) sum += __shfl_xor_sync(~0u, sum, o);
 		const float mean = sum * inv_c;
 		float sq = 0.f;
 		#pragma unroll
 		for (int i = 0; i < NCH; ++i)
-			if (lane + i * 32 < chunks) {
+			if (li + i * LPR < chunks) {
 				#pragma unroll
 				for (int j = 0; j < 8; ++j) { v[i][j] -= mean; sq = fmaf(v[i][j], v[i][j], sq); }
 			}
 		#pragma unroll
-		for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(~0u, sq, o);
+		for (int o = LPR / 2; o; o >>= 1) sq += __shfl_xor_sync(~0u, sq, o);
 		const float rstd = rsqrtf(sq * inv_c + eps);
-		#pragma unroll
-		for (int i = 0; i < NCH; ++i) {
-			const int ch = lane + i * 32;
-			if (ch < chunks) {
-				float t[8];
-				#pragma unroll
-				for (int j = 0; j < 8; ++j) t[j] = fmaf(v[i][j] * rstd, ga[i][j], be[i][j]);
-				*reinterpret_cast<uint4*>(y + row * ld_out + ch * 8) = f_to_h8(t);
+		if (row < rows) {
+			#pragma unroll
+			for (int i = 0; i < NCH; ++i) {
+				const int ch = li + i * LPR;
+				if (ch < chunks) {
+					float t[8];
+					#pragma unroll
+					for (int j = 0; j < 8; ++j) t[j] = fmaf(v[i][j] * rstd, ga[i][j], be[i][j]);
+					*reinterpret_cast<uint4*>(y + row * ld_out + ch * 8) = f_to_h8(t);
+				}
 			}
 		}
 		#pragma unroll
 		for (int i = 0; i < NCH; ++i) cur[i] = nxt[i];
 	}
+}
+
+template <int LPR, int NCH>
+static void layernorm_fast_launch(cudaStream_t s, const __half* x, __half* y, long long rows, int C, long long ldi, long long ldo,
+	const float* g, const float* b, float eps)
+{
+	static int bps = 0;       // resident blocks per SM of this instantiation
+	if (!bps) {
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, layernorm_fast_kernel<LPR, NCH>, 256, 0) != cudaSuccess || bps < 1) { cudaGetLastError(); bps = 1; }
+	}
+	constexpr int RW = 32 / LPR;
+	const long long groups = (rows + RW - 1) / RW;
+	const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((groups + 7) / 8, 148LL * bps));
+	layernorm_fast_kernel<LPR, NCH><<<grid, 256, 0, s>>>(x, y, rows, C, ldi, ldo, g, b, eps);
+}
+
+// lanes per row and chunks per lane for a row of `chunks` 8-element chunks: the fewest chunks per lane (<= 5) with no idle lane
+static bool layernorm_fast_dispatch(cudaStream_t s, const __half* x, __half* y, long long rows, int C, long long ldi, long long ldo,
+	const float* g, const float* b, float eps)
+{
+	const int chunks = C / 8;
+	#define LN_TRY(LPR, NCH) if (chunks <= LPR * NCH && chunks > LPR * (NCH - 1)) { layernorm_fast_launch<LPR, NCH>(s, x, y, rows, C, ldi, ldo, g, b, eps); return true; }
+	static const int mode = getenv("GGML_B200_LN_MODE") ? atoi(getenv("GGML_B200_LN_MODE")) : 0;   // 1: 3 chunks per lane (fewer registers, some idle lanes)
+	if (mode == 1 && chunks % 5 == 0 && chunks / 5 <= 16) { switch (chunks / 5) { case 8: LN_TRY(16, 3) break; case 16: LN_TRY(32, 3) break; } }
+	if (chunks % 5 == 0 && chunks / 5 <= 32 && ((chunks / 5) & (chunks / 5 - 1)) == 0) {      // 40 * 2^k chunks: 320, 640, 1280 (and 40, 80, 160)
+		switch (chunks / 5) { case 1: LN_TRY(1, 5) break; case 2: LN_TRY(2, 5) break; case 4: LN_TRY(4, 5) break; case 8: LN_TRY(8, 5) break;
+			case 16: LN_TRY(16, 5) break; case 32: LN_TRY(32, 5) break; }
+	}
+	if (chunks % 3 == 0 && chunks / 3 <= 32 && ((chunks / 3) & (chunks / 3 - 1)) == 0) {      // 96 chunks: 768 (CLIP ViT-L)
+		switch (chunks / 3) { case 8: LN_TRY(8, 3) break; case 16: LN_TRY(16, 3) break; case 32: LN_TRY(32, 3) break; }
+	}
+	if ((chunks & (chunks - 1)) == 0) {                                                        // powers of two: 1024 (OpenCLIP ViT-H), 2048
+		switch (chunks) { case 8: LN_TRY(8, 1) break; case 16: LN_TRY(16, 1) break; case 32: LN_TRY(32, 1) break; case 64: LN_TRY(32, 2) break; case 128: LN_TRY(32, 4) break; }
+	}
+	LN_TRY(32, 1) LN_TRY(32, 2) LN_TRY(32, 3) LN_TRY(32, 4) LN_TRY(32, 5)
+	#undef LN_TRY
+	return false;
 }
 
 // scalar fallback for row lengths that are not multiples of 8 (or unaligned rows)
@@ -822,14 +894,7 @@ static void layernorm_launch(cudaStream_t s, const void* x, void* y, long long r
 	bool vec = C % 8 == 0 && ldi % 8 == 0 && ldo % 8 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0 && C <= 2048;
 	if (!vec) { layernorm_scalar_kernel<TI, TO><<<grid, wpb * 32, 0, s>>>((const TI*)x, (TO*)y, rows, C, ldi, ldo, g, b, eps); return; }
 	if (sizeof(TI) == 2 && sizeof(TO) == 2 && C <= 256 * 5 && (!g || !((uintptr_t)g & 15)) && (!b || !((uintptr_t)b & 15))) {
-		// grid-stride fast path: one row per warp until the chip holds 16 blocks of 8 warps per SM, more rows per warp beyond
-		unsigned fg = (unsigned)std::min<long long>((rows + wpb - 1) / wpb, 148LL * 16);
-		fg = std::max(fg, 1u);
-		if (C <= 256) layernorm_fast_kernel<1><<<fg, wpb * 32, 0, s>>>((const __half*)x, (__half*)y, rows, C, ldi, ldo, g, b, eps);
-		else if (C <= 512) layernorm_fast_kernel<2><<<fg, wpb * 32, 0, s>>>((const __half*)x, (__half*)y, rows, C, ldi, ldo, g, b, eps);
-		else if (C <= 768) layernorm_fast_kernel<3><<<fg, wpb * 32, 0, s>>>((const __half*)x, (__half*)y, rows, C, ldi, ldo, g, b, eps);
-		else layernorm_fast_kernel<5><<<fg, wpb * 32, 0, s>>>((const __half*)x, (__half*)y, rows, C, ldi, ldo, g, b, eps);
-		return;
+		if (layernorm_fast_dispatch(s, (const __half*)x, (__half*)y, rows, C, ldi, ldo, g, b, eps)) return;
 	}
 	if (C <= 256 * 2) layernorm_kernel<TI, TO, 2><<<grid, wpb * 32, 0, s>>>((const TI*)x, (TO*)y, rows, C, ldi, ldo, g, b, eps);
 	else if (C <= 256 * 5) layernorm_kernel<TI, TO, 5><<<grid, wpb * 32, 0, s>>>((const TI*)x, (TO*)y, rows, C, ldi, ldo, g, b, eps);
