@@ -414,6 +414,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 	uint32_t* tmem_slot = (uint32_t*)(res_full + 1);
 
 	const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
+	if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[6] = clock64();          // kernel entry
 	const int csize = TWO_SM ? 2 : p.cm * p.cn;
 	const int crank = csize > 1 ? (int)cluster_ctarank() : 0;
 	const int pr = TWO_SM ? crank : 0;               // rank inside the CTA pair (0 = leader, issues the MMAs)
@@ -714,6 +715,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 	tc_fence_before();
 	__syncthreads();
 	if (csize > 1) cluster_sync_all();                 // no CTA leaves while a peer may still signal its barriers
+	if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[7] = clock64();          // kernel exit
 	if (warp == 9) { tc_fence_after(); if (TWO_SM) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
@@ -1062,6 +1064,7 @@ void gemm_tc_free(GemmTC* g)
 		cudaDeviceSynchronize();
 		cudaMemcpy(h, g->p.trace, sizeof(h), cudaMemcpyDeviceToHost);
 		fprintf(stderr, "[ggml_b200] epilogue timeline of CTA 0 (cycles since its first tile; M=%d N=%d K=%d BN=%d): start | bias+store-drain+bar | acc ready | drained | fence+bar | stores issued\n", g->p.M, g->p.N, g->p.K, g->p.BN);
+		fprintf(stderr, "  kernel entry %lld, exit %lld (same origin)\n", h[6] - h[0], h[7] - h[0]);
 		for (int t = 0; t < 16 && h[t * 8]; ++t) {
 			fprintf(stderr, "  tile %2d:", t);
 			for (int e = 0; e < 6; ++e) fprintf(stderr, " %8lld", h[t * 8 + e] - h[0]);

@@ -259,7 +259,9 @@ MLTensor* mlb_clip_text_proj(MLCtx* C, MLTensor* x, int i_tok_end)
 	int d = (int)x->ne[0];
 	MLTensor* p = N("text_proj", ggml_new_tensor_2d(C->cp, GGML_TYPE_F32, d, d));
 	p = ggml_cont(C->cc, ggml_transpose(C->cc, p));
-	x = ggml_view_1d(C->cc, x, d, x->nb[1] * i_tok_end);   /* features of the first end-of-text token */
+	/* i_tok_end >= 0: features of the first end-of-text token only (clip.c:418-437). i_tok_end < 0: project every
+	   position; the caller picks the row it needs, so the graph does not depend on the prompt length. */
+	if (i_tok_end >= 0) x = ggml_view_1d(C->cc, x, d, x->nb[1] * i_tok_end);
 	return ggml_mul_mat(C->cc, p, x);
 }
 
@@ -274,16 +276,19 @@ int clip_text_encode(ClipState* S, MLCtx* C, const ClipParams* P, const char* tp
 	tokens[n_tok + 1] = P->tok_end;
 	for (int i = n_tok + 2; i < P->n_token; ++i) tokens[i] = P->tok_pad;
 
-	/* the pooled-feature graph depends on the EOS position: rebuilt only when that changes */
+	/* The reference's pooled-feature graph depends on the EOS position (view at row n_tok + 1, clip.c:431), which would
+	   rebuild the graph -- and re-upload the encoder's weights -- whenever the prompt length changes (every generation:
+	   prompt and negative prompt alternate). Here every position is projected (row-wise independent, same arithmetic
+	   per row) and the EOS row is read back, so one graph serves all prompts. */
 	bool reuse = C->prepared && S->ctx == C && S->par == P && S->clip_skip == clip_skip && S->norm == norm &&
-		S->with_feat == (feat != NULL) && (!feat || S->n_tok_feat == (int)n_tok);
+		S->with_feat == (feat != NULL);
 	if (!reuse) {
 		mlctx_begin(C, "CLIP text encode");
 		S->t_tok = mlctx_input_new(C, "tokens", GGML_TYPE_I32, P->n_token, 1, 1, 1);
 		S->t_embed = mlb_clip_text(C, S->t_tok, P, clip_skip, norm);
 		MLTensor* result = S->t_embed;
 		S->t_feat = NULL;
-		if (feat) result = S->t_feat = mlb_clip_text_proj(C, S->t_embed, n_tok + 1);
+		if (feat) result = S->t_feat = mlb_clip_text_proj(C, S->t_embed, -1);
 		else ggml_set_output(S->t_embed);
 		mlctx_tensor_add(C, "text", result);
 		C->c.tprefix = tprefix;
@@ -298,7 +303,7 @@ int clip_text_encode(ClipState* S, MLCtx* C, const ClipParams* P, const char* tp
 	}
 	if (feat) {
 		ht_resize(feat, P->d_embed, 1, 1, 1);
-		ggml_backend_tensor_get(S->t_feat, feat->d, 0, ht_count(feat) * sizeof(float));
+		ggml_backend_tensor_get(S->t_feat, feat->d, (size_t)(n_tok + 1) * P->d_embed * sizeof(float), ht_count(feat) * sizeof(float));
 	}
 	return 1;
 }

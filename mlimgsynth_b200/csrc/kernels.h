@@ -10,6 +10,7 @@ void k_copy(cudaStream_t s, const View& dst, const View& src);
 void k_binary(cudaStream_t s, BinOp op, const View& dst, const View& a, const View& b);
 void k_unary(cudaStream_t s, UnaryOp op, float param, const View& dst, const View& src);
 void k_upscale(cudaStream_t s, const View& dst, const View& src);
+void k_spin(cudaStream_t s, int microseconds);      // profiling aid: keeps the stream busy while the next launches are enqueued
 void k_softmax_rows(cudaStream_t s, const View& dst, const View& src, bool causal, int n_past);
 // rows of f32 scores -> f16 probabilities softmax(scale * s) (wide-head attention as two tensor-core GEMMs)
 bool k_softmax_f32_f16_supported(int64_t cols);

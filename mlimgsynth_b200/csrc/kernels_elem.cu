@@ -181,6 +181,18 @@ void k_unary(cudaStream_t s, UnaryOp op, float param, const View& dst, const Vie
 	g_stats.kernel_launches++;
 }
 
+// ------------------------------------------------------------------ profiling aid
+// One thread spins for a fixed time. The profiled pass (planner.cpp) puts it in front of every timed step so that the
+// step's launches are already queued on the device when its start event fires: the event pair then measures the
+// kernel, not the host's launch latency (5-10 us for a cluster launch with four tensor maps in its parameters).
+__global__ void spin_kernel(long long ns)
+{
+	unsigned long long t0, t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+	do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); } while ((long long)(t - t0) < ns);
+}
+void k_spin(cudaStream_t s, int microseconds) { spin_kernel<<<1, 1, 0, s>>>((long long)microseconds * 1000); }
+
 // ------------------------------------------------------------------ nearest upscale (mlblock_nn.c:122)
 __global__ void upscale_kernel(V4 dst, V4 src, Iter4 it, int f0, int f1)
 {
@@ -614,6 +626,79 @@ gn_apply_fast_kernel(const __half* __restrict__ x, __half* __restrict__ y, long 
 		*reinterpret_cast<uint4*>(obase + p * opix_stride) = apply(*reinterpret_cast<const uint4*>(base + p * pix_stride));
 }
 
+
+// ---- small tensors (f16, channels-last): ONE kernel, one block per (image, group). The block's slice (HW pixels x cpg
+// channels, <= GN_SMALL_MAXV half2 per thread) is read once into registers, reduced exactly in two passes (mean, then
+// centred sum of squares, f32 per thread, combined in double across the block) and written back normalised: no
+// statistics buffer, no atomics, no second read. Used for the smallest levels (8x8, 16x16x640 per image), where the
+// two-kernel path is launch-latency bound.
+constexpr int GN_SMALL_MAXV = 64;
+template <bool SILU, int NV>     // NV: half2 values per thread (upper bound, compile time so that they stay in registers)
+__global__ void __launch_bounds__(256)
+gn_small_kernel(const __half* __restrict__ x, __half* __restrict__ y, int HW, int cpg, int groups,
+	long long img_stride, long long pix_stride, long long oimg_stride, long long opix_stride,
+	const float* __restrict__ gamma, const float* __restrict__ beta, float eps, unsigned c2n_mul)
+{
+	__shared__ double red[8];
+	const int g = blockIdx.x, n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	const int c2n = cpg >> 1, total = HW * c2n;                 // half2 units per pixel of this group / in the slice
+	const __half* xb = x + n * img_stride + (long long)g * cpg;
+	__half* yb = y + n * oimg_stride + (long long)g * cpg;
+	// element e = tid + 256 i of the slice is (pixel p = e / c2n, channel pair c2): one multiply-high instead of a division
+	__half2 v[NV];
+	float sum = 0.f;
+	#pragma unroll
+	for (int i = 0; i < NV; ++i) {
+		const int e = tid + i * 256;
+		if (e < total) {
+			const int p = c2n_mul ? (int)__umulhi((unsigned)e, c2n_mul) : e, c2 = e - p * c2n;
+			v[i] = *reinterpret_cast<const __half2*>(xb + p * pix_stride + 2 * c2);
+			const float2 f = __half22float2(v[i]);
+			sum += f.x + f.y;
+		}
+	}
+	auto block_sum = [&](float s) -> double {
+		#pragma unroll
+		for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(~0u, s, o);
+		__syncthreads();                                         // red[] of the previous reduction has been consumed
+		if (lane == 0) red[w] = (double)s;
+		__syncthreads();
+		double t = 0.0;
+		#pragma unroll
+		for (int i = 0; i < 8; ++i) t += red[i];
+		return t;
+	};
+	const double cnt = (double)HW * cpg;
+	const float mean = (float)(block_sum(sum) / cnt);
+	float sq = 0.f;
+	#pragma unroll
+	for (int i = 0; i < NV; ++i)
+		if (tid + i * 256 < total) { const float2 f = __half22float2(v[i]); const float a = f.x - mean, b = f.y - mean; sq = fmaf(a, a, sq); sq = fmaf(b, b, sq); }
+	const float rstd = (float)(1.0 / sqrt(block_sum(sq) / cnt + (double)eps));
+	#pragma unroll
+	for (int i = 0; i < NV; ++i) {
+		const int e = tid + i * 256;
+		if (e < total) {
+			const int p = c2n_mul ? (int)__umulhi((unsigned)e, c2n_mul) : e, c2 = e - p * c2n, c = g * cpg + 2 * c2;
+			const float g0 = gamma ? gamma[c] : 1.f, g1 = gamma ? gamma[c + 1] : 1.f;
+			const float b0 = (gamma && beta) ? beta[c] : 0.f, b1 = (gamma && beta) ? beta[c + 1] : 0.f;
+			const float2 f = __half22float2(v[i]);
+			float t0 = fmaf((f.x - mean) * rstd, g0, b0), t1 = fmaf((f.y - mean) * rstd, g1, b1);
+			if (SILU) { t0 = silu_tanh(t0); t1 = silu_tanh(t1); }
+			*reinterpret_cast<__half2*>(yb + p * opix_stride + 2 * c2) = __floats2half2_rn(t0, t1);
+		}
+	}
+}
+
+template <int NV>
+static void gn_small_launch(cudaStream_t s, bool silu, dim3 grid, const __half* x, __half* y, int HW, int cpg, int groups,
+	long long is, long long ps, long long ois, long long ops, const float* gamma, const float* beta, float eps)
+{
+	const unsigned c2n = (unsigned)(cpg / 2), mul = c2n <= 1 ? 0u : (unsigned)((0x100000000ull + c2n - 1) / c2n);   // exact while e * c2n < 2^32
+	if (silu) gn_small_kernel<true, NV><<<grid, 256, 0, s>>>(x, y, HW, cpg, groups, is, ps, ois, ops, gamma, beta, eps, mul);
+	else gn_small_kernel<false, NV><<<grid, 256, 0, s>>>(x, y, HW, cpg, groups, is, ps, ois, ops, gamma, beta, eps, mul);
+}
+
 void k_groupnorm(cudaStream_t s, const View& dst, const View& src, const float* gamma, const float* beta,
 	int groups, float eps, bool silu, double* stats)
 {
@@ -623,6 +708,20 @@ void k_groupnorm(cudaStream_t s, const View& dst, const View& src, const float* 
 		B200_FATAL("k_groupnorm: unsupported layout (C=%d)", C);
 	if (src.dt == DT_F16 && dst.dt == DT_F16 && !((uintptr_t)src.ptr & 15) && !((uintptr_t)dst.ptr & 15) &&
 		src.st[0] % 8 == 0 && dst.st[0] % 8 == 0 && src.st[3] % 8 == 0 && dst.st[3] % 8 == 0) {
+		// small slices: single pass, one block per (image, group)
+		static const bool small_on = !(getenv("GGML_B200_GN_SMALL") && atoi(getenv("GGML_B200_GN_SMALL")) == 0);
+		const long long slice2 = HW * (cpg / 2);                 // half2 units per (image, group)
+		if (small_on && C == groups * cpg && cpg % 2 == 0 && slice2 <= 256LL * 12 && HW < (1 << 24)) {          // measured: beyond ~12 values per thread the two-kernel path wins
+			dim3 grid((unsigned)groups, (unsigned)N);
+			const __half* xp = (const __half*)src.ptr; __half* yp = (__half*)dst.ptr;
+			const int nv = (int)((slice2 + 255) / 256);
+			if (nv <= 8) gn_small_launch<8>(s, silu, grid, xp, yp, (int)HW, cpg, groups, src.st[3], src.st[0], dst.st[3], dst.st[0], gamma, beta, eps);
+			else if (nv <= 16) gn_small_launch<16>(s, silu, grid, xp, yp, (int)HW, cpg, groups, src.st[3], src.st[0], dst.st[3], dst.st[0], gamma, beta, eps);
+			else if (nv <= 32) gn_small_launch<32>(s, silu, grid, xp, yp, (int)HW, cpg, groups, src.st[3], src.st[0], dst.st[3], dst.st[0], gamma, beta, eps);
+			else gn_small_launch<GN_SMALL_MAXV>(s, silu, grid, xp, yp, (int)HW, cpg, groups, src.st[3], src.st[0], dst.st[3], dst.st[0], gamma, beta, eps);
+			g_stats.kernel_launches++;
+			return;
+		}
 		const int chunks = C / 8;
 		const int nslabs = (chunks + 255) / 256, slab_chunks = (chunks + nslabs - 1) / nslabs;
 		const int planes = std::max(1, 256 / slab_chunks), threads = slab_chunks * planes;

@@ -499,6 +499,79 @@ void Builder::plan_mul_mat(ggml_tensor* t)
 	// Sibling projections of the same activation without bias / activation / residual (q, k, v of a self-attention,
 	// mlblock_nn.c:199-203; the k and v projections of the text context in every cross-attention, unet.c:110-145) run
 	// as ONE GEMM over the concatenated weight rows: the activation is streamed once instead of once per projection.
+	// Biased sibling projections of the same (activated) vector: the time-embedding projection of every resnet,
+	// emb_layers = linear(silu(emb)) (mlblock_nn.c:139-144), 22 launches with M = images in SD1.x. Each resnet builds its own
+	// silu node, so siblings are matched through the unary's source. One GEMM over the concatenated weight rows and biases;
+	// the members read column slices of its output (the conv epilogue's per-image vector takes any row pitch).
+	if (tc_ok && !env_flag("GGML_B200_NO_PROJ_FUSION") && !env_flag("GGML_B200_NO_EMB_FUSION") && b->ne[1] * b->ne[2] * b->ne[3] <= 256) {
+		const bool b_unary = b->op == GGML_OP_UNARY;
+		const ggml_tensor* bsrc = b_unary ? b->src[0] : b;
+		auto same_input = [&](const ggml_tensor* x) {
+			if (x == b) return true;
+			if (!b_unary || x->op != GGML_OP_UNARY || x->src[0] != bsrc || x->op_params[0] != b->op_params[0]) return false;
+			for (int i = 0; i < 4; ++i) if (x->ne[i] != b->ne[i]) return false;
+			return true;
+		};
+		auto biased = [&](ggml_tensor* u, ggml_tensor** addp) {
+			const ggml_tensor* w = u->src[0];
+			if (u->op != GGML_OP_MUL_MAT || !same_input(u->src[1]) || done.count(u) || (u->flags & GGML_TENSOR_FLAG_OUTPUT)) return false;
+			if (w->op != GGML_OP_NONE || w->type != GGML_TYPE_F16 || w->ne[0] != K || w->ne[2] != 1 || w->ne[3] != 1 || (w->nb[1] / 2) % 8 || w->ne[1] % 8) return false;
+			ggml_tensor* nx;
+			if (!single_user(u, &nx) || nx->op != GGML_OP_ADD || nx->src[0] != u || (nx->flags & GGML_TENSOR_FLAG_OUTPUT)) return false;
+			if (!is_channel_vec(nx->src[1], u, 0)) return false;
+			auto it = users.find(nx);
+			if (it == users.end() || it->second.empty()) return false;
+			for (ggml_tensor* q : it->second) if (q->op != GGML_OP_RESHAPE) return false;      // no activation / residual to absorb: the sum is used as a vector
+			*addp = nx;
+			return true;
+		};
+		std::vector<ggml_tensor*> grp, adds;
+		auto scan = [&](const ggml_tensor* in) {
+			auto it = users.find(in);
+			if (it == users.end()) return;
+			for (ggml_tensor* u : it->second) { ggml_tensor* ad; if (std::find(grp.begin(), grp.end(), u) == grp.end() && biased(u, &ad)) { grp.push_back(u); adds.push_back(ad); } }
+		};
+		if (b_unary) { auto it = users.find(bsrc); if (it != users.end()) for (ggml_tensor* q : it->second) if (same_input(q)) scan(q); }
+		else scan(b);
+		if (grp.size() >= 2 && std::find(grp.begin(), grp.end(), t) != grp.end()) {
+			int64_t n_total = 0;
+			for (ggml_tensor* u : grp) n_total += u->src[0]->ne[1];
+			int64_t ne_w[4] = { K, n_total, 1, 1 }, ne_b[4] = { n_total, 1, 1, 1 };
+			PT wcat = new_pt(DT_F16, ne_w, BUF_PERSIST), bcat = new_pt(DT_F32, ne_b, BUF_PERSIST);
+			PT A = as_gemm_rows(pb);
+			int64_t rows, pitch; rows_uniform(A, rows, pitch);
+			PT out; out.dt = DT_F16;
+			out.ne[0] = n_total; out.ne[1] = b->ne[1]; out.ne[2] = b->ne[2]; out.ne[3] = b->ne[3];
+			contiguous_strides(out);
+			out.buf = new_buf(BUF_ARENA, (size_t)out.numel() * 2);
+			int64_t col = 0;
+			for (size_t i = 0; i < grp.size(); ++i) {
+				const ggml_tensor* w = grp[i]->src[0];
+				const ggml_tensor* bl = strip_reshape(adds[i]->src[1]);
+				PT sub = wcat; sub.ne[1] = w->ne[1]; sub.off = col * K;
+				Step ps; ps.kind = S_COPY; ps.name = "proj_weight_concat"; ps.out = sub; ps.in[0] = get(w); ps.n_in = 1; ps.leaf = w;
+				P->prep.push_back(ps);
+				PT bsub = bcat; bsub.ne[0] = w->ne[1]; bsub.off = col;
+				PT bsrc_pt = get(bl); bsrc_pt.ne[0] = w->ne[1]; bsrc_pt.ne[1] = bsrc_pt.ne[2] = bsrc_pt.ne[3] = 1; bsrc_pt.st[0] = 1;
+				Step pb2; pb2.kind = S_COPY; pb2.name = "proj_bias_concat"; pb2.out = bsub; pb2.in[0] = bsrc_pt; pb2.n_in = 1; pb2.leaf = bl;
+				P->prep.push_back(pb2);
+				col += w->ne[1];
+			}
+			Step s; s.kind = S_GEMM_TC; s.name = "linear_fused";
+			s.in[0] = A; s.in[1] = wcat; s.n_in = 2; s.out = out;
+			s.M = rows; s.N = n_total; s.K = K; s.lda = pitch; s.ldb = K; s.ldc = n_total;
+			s.bias = bcat; s.has_bias = true;
+			P->steps.push_back(s);
+			col = 0;
+			for (size_t i = 0; i < grp.size(); ++i) {
+				PT v = out; v.ne[0] = grp[i]->src[0]->ne[1]; v.off = col;
+				col += v.ne[0];
+				done[grp[i]] = true;
+				finish(adds[i], v);
+			}
+			return;
+		}
+	}
 	if (tc_ok && !env_flag("GGML_B200_NO_PROJ_FUSION")) {
 		auto plain = [&](const ggml_tensor* u) {
 			const ggml_tensor* w = u->src[0];
@@ -1144,6 +1217,7 @@ static void plan_run_profiled(Plan* P)
 	if (P->zero_bytes) CUDA_CHECK(cudaMemsetAsync((char*)P->arena + P->bufs[P->zero_buf].off, 0, P->zero_bytes, st));
 	for (Step& s : P->steps) {
 		uint64_t l0 = g_stats.kernel_launches;
+		k_spin(st, 25);                        // the step's launches queue up behind it: host launch latency stays out of the timing
 		CUDA_CHECK(cudaEventRecord(e0, st));
 		run_step(P, s, st);
 		CUDA_CHECK(cudaEventRecord(e1, st));

@@ -74,7 +74,8 @@ def test_upsample(ref, eng):
 
 
 # ---------------------------------------------------------------- norms and element-wise
-@pytest.mark.parametrize("W,H,C,N", [(64, 64, 320, 1), (8, 8, 1280, 2), (16, 16, 960, 1), (32, 32, 128, 1), (5, 3, 64, 1)])
+@pytest.mark.parametrize("W,H,C,N", [(64, 64, 320, 1), (8, 8, 1280, 2), (16, 16, 960, 1), (32, 32, 128, 1), (5, 3, 64, 1),
+                                     (32, 32, 640, 2), (64, 64, 320, 2), (32, 32, 1920, 1), (16, 16, 2560, 3), (24, 40, 320, 1)])
 def test_groupnorm_silu(ref, eng, W, H, C, N):
     def build(b):
         x = b.groupnorm32(b.inp(N, C, H, W, scale=2.0))
@@ -82,7 +83,7 @@ def test_groupnorm_silu(ref, eng, W, H, C, N):
     check(build, ref, eng, OP_TOL)
 
 
-@pytest.mark.parametrize("rows,C", [(4096, 320), (77, 768), (64, 1280), (3, 2048), (10, 100)])
+@pytest.mark.parametrize("rows,C", [(4096, 320), (77, 768), (64, 1280), (3, 2048), (10, 100), (1021, 640), (301, 1024), (5, 1280), (7, 320), (130, 160)])
 def test_layernorm(ref, eng, rows, C):
     check(lambda b: b.layer_norm(b.inp(rows, C, scale=3.0)), ref, eng, OP_TOL)
 
@@ -282,5 +283,21 @@ def test_projection_fusion_matches_unfused(ref, eng, monkeypatch):
     (r,), (fused,) = run_both(build, ref, eng, 4)
     monkeypatch.setenv("GGML_B200_NO_PROJ_FUSION", "1")
     (_,), (plain,) = run_both(build, ref, eng, 4)
+    assert max_rel_err(fused, r) <= BLOCK_TOL and max_rel_err(plain, r) <= BLOCK_TOL
+    assert max_rel_err(fused, plain) <= OP_TOL
+
+
+def test_embedding_projection_fusion_matches_unfused(ref, eng, monkeypatch):
+    """The time-embedding projections of several resnets (each with its own silu(emb) node, different widths, with bias)
+    run as one GEMM over concatenated weights and biases, or one by one."""
+    def build(b):
+        emb = b.inp(3, 1280)
+        h = b.conv2d(b.inp(3, 4, 16, 16), 128)
+        h = b.resnet(h, emb, 128)
+        h = b.resnet(h, emb, 256)
+        return b.resnet(h, emb, 192)
+    (r,), (fused,) = run_both(build, ref, eng, 5)
+    monkeypatch.setenv("GGML_B200_NO_EMB_FUSION", "1")
+    (_,), (plain,) = run_both(build, ref, eng, 5)
     assert max_rel_err(fused, r) <= BLOCK_TOL and max_rel_err(plain, r) <= BLOCK_TOL
     assert max_rel_err(fused, plain) <= OP_TOL

@@ -1,6 +1,9 @@
 """Turn ncu outputs brought back in gpurun_out/ into the tracked summaries under profiles/.
   summarize_ncu.py launches <launches.csv> <out.md>          per-kernel share of one generation (gpu__time_duration)
-  summarize_ncu.py full <file.ncu-rep> <out.md>               key metrics of every captured launch (ncu --set full)"""
+  summarize_ncu.py full <file.ncu-rep> <out.md>               key metrics of every captured launch (ncu --set full)
+  summarize_ncu.py traffic <gemm_traffic.csv> <steps.log> <out.md> <out.json>
+                                                              DRAM bytes / tensor-pipe activity of every GEMM + conv launch of one UNet
+                                                              evaluation (ncu --metrics ...), joined with the shapes of the step log"""
 import csv, subprocess, sys, collections, re, io
 
 def short(name):
@@ -73,5 +76,41 @@ def full(path, out):
                     cells.append(v)
             f.write("| %d | `%s` | %s |\n" % (j, short(r[idx["Kernel Name"]])[:60], " | ".join(cells)))
 
+def traffic(path, steps_log, out_md, out_json):
+    import json
+    lines = [l for l in open(path) if not l.startswith("==")]
+    rows = collections.OrderedDict()
+    for r in csv.DictReader(io.StringIO("".join(lines))):
+        d = rows.setdefault(r["ID"], {"name": r["Kernel Name"], "grid": r["Grid Size"]})
+        d[r["Metric Name"]] = (float(r["Metric Value"].replace(",", "")), r["Metric Unit"])
+    tob = lambda x: x[0] * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[x[1]]
+    tus = lambda x: x[0] / 1e3 if x[1].startswith("n") else x[0] * 1e3 if x[1].startswith("m") else x[0]
+    steps = []
+    for l in open(steps_log):
+        m = re.match(r"step (\S+)\s+kind\s+(\d+)\s+([\d.]+) us\s+out\[([\d,]+)\] in0\[([\d,]+)\] M(\d+) N(\d+) K(\d+)", l)
+        if m and m.group(2) in ("14", "15"):
+            steps.append((m.group(1), int(m.group(6)), int(m.group(7)), int(m.group(8)), int(m.group(2))))
+    assert len(steps) == len(rows), (len(steps), len(rows))
+    agg = collections.OrderedDict(); tot_b = tot_us = tot_fl = 0.0
+    for s, v in zip(steps, rows.values()):
+        us = tus(v["gpu__time_duration.sum"]); by = tob(v["dram__bytes_read.sum"]) + tob(v["dram__bytes_write.sum"])
+        tp = v["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"][0]
+        fl = 2.0 * s[1] * s[2] * s[3]
+        a = agg.setdefault(s, [0, 0.0, 0.0, 0.0]); a[0] += 1; a[1] += us; a[2] += by; a[3] += tp
+        tot_b += by; tot_us += us; tot_fl += fl
+    with open(out_md, "w") as f:
+        f.write("# ncu: every tcgen05 GEMM / implicit-conv launch of one SD1.5 UNet evaluation (batch 16, eager)\n\n")
+        f.write("`--metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active...` "
+                "(durations are cold-cache and serialised).\n\n")
+        f.write("%d launches, %.2f ms, %.2f GB of DRAM traffic = %.1f MB per launch; %.1f TFLOP\n\n" % (len(rows), tot_us / 1e3, tot_b / 1e9, tot_b / 1e6 / len(rows), tot_fl / 1e12))
+        f.write("| op | M | N | K | launches | us each | TFLOP/s | tensor pipe % | DRAM MB each |\n|---|---:|---:|---:|---:|---:|---:|---:|---:|\n")
+        for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
+            n = a[0]
+            f.write("| %s | %d | %d | %d | %d | %.1f | %.0f | %.1f | %.1f |\n" % (k[0], k[1], k[2], k[3], n, a[1] / n, 2.0 * k[1] * k[2] * k[3] / (a[1] / n) / 1e6, a[3] / n, a[2] / n / 1e6))
+    json.dump({"what": "dram__bytes_read.sum + dram__bytes_write.sum over all tcgen05 GEMM/conv launches of one SD1.5 batch-16 UNet evaluation (ncu, one capture)",
+               "launches": len(rows), "dram_bytes_total": tot_b, "dram_bytes_per_launch": tot_b / len(rows), "ncu_time_us_total": tot_us, "flop_total": tot_fl},
+              open(out_json, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
