@@ -612,7 +612,19 @@ static int decode_dev(MLIS_Ctx* S, int lw, int lh, int n)
 	int f = S->vae_p->f_down, w = lw * f, h = lh * f;
 	size_t per = (size_t)w * h * 3;
 	dev_reserve(&S->image_dev, &S->image_dev_n, per * n);
-	for (int i = 0; i < n; ++i) {
+	/* untiled VAE decode: all images of the batch in one graph run, in chunks of <= 2^17 latent pixels (8 images of 512x512) */
+	int done_n = 0;
+	if (!(S->flags & CF_USE_TAE) && n > 1) {
+		int chunk = (1 << 17) / (lw * lh); if (chunk > n) chunk = n;
+		while (chunk >= 2 && n - done_n >= chunk) {
+			int r = sdvae_decode_batch(&S->st_vdec, graph_ctx_init(S, &S->ctx_vdec), S->vae_p, S->latent_dev + (size_t)done_n * lw * lh * 4, lw, lh, chunk,
+				S->image_dev + per * done_n, S->vae_tile);
+			if (r < 0) return r;
+			if (r == 0) break;
+			done_n += chunk;
+		}
+	}
+	for (int i = done_n; i < n; ++i) {
 		const float* l = S->latent_dev + (size_t)i * lw * lh * 4;
 		float* im = S->image_dev + per * i;
 		if (S->flags & CF_USE_TAE) CHECK(sdtae_decode(&S->st_tdec, graph_ctx_init(S, &S->ctx_tdec), S->tae_p, l, lw, lh, im));

@@ -133,13 +133,13 @@ MLTensor* mlb_sdtae_decoder(MLCtx* C, MLTensor* x, const SdTaeParams* P)
 }
 
 /* ---- runners ---- */
-static int codec_prepare(CodecState* S, MLCtx* C, int kind, int n0, int n1, const void* P)
+static int codec_prepare(CodecState* S, MLCtx* C, int kind, int n0, int n1, int nb, const void* P)
 {
-	if (C->prepared && S->ctx == C && S->kind == kind && S->n0 == n0 && S->n1 == n1) return 1;
+	if (C->prepared && S->ctx == C && S->kind == kind && S->n0 == n0 && S->n1 == n1 && S->nb == nb) return 1;
 	static const char* names[] = { "", "VAE decode", "VAE encode", "TAE decode", "TAE encode" };
 	mlctx_begin(C, names[kind]);
 	int cin = (kind == CODEC_VAE_DEC || kind == CODEC_TAE_DEC) ? 4 : 3;
-	S->t_in = mlctx_input_new(C, "in", GGML_TYPE_F32, n0, n1, cin, 1);
+	S->t_in = mlctx_input_new(C, "in", GGML_TYPE_F32, n0, n1, cin, nb);
 	switch (kind) {
 	case CODEC_VAE_DEC: S->t_out = mlb_sdvae_decoder(C, S->t_in, P); C->c.tprefix = "vae"; break;
 	case CODEC_VAE_ENC: S->t_out = mlb_sdvae_encoder(C, S->t_in, P); C->c.tprefix = "vae"; break;
@@ -147,7 +147,7 @@ static int codec_prepare(CodecState* S, MLCtx* C, int kind, int n0, int n1, cons
 	case CODEC_TAE_ENC: S->t_out = mlb_sdtae_encoder(C, S->t_in, P); mlctx_tensor_add(C, "encoder.layers", S->t_out); C->c.tprefix = "tae"; break;
 	}
 	CHECK(mlctx_prep(C));
-	S->ctx = C; S->kind = kind; S->n0 = n0; S->n1 = n1;
+	S->ctx = C; S->kind = kind; S->n0 = n0; S->n1 = n1; S->nb = nb;
 	return 1;
 }
 
@@ -207,10 +207,27 @@ int sdvae_decode(CodecState* S, MLCtx* C, const VaeParams* P, const float* laten
 {
 	const int f = P->f_down, k = 8;
 	int n0 = tile_extent(tile_px, f, k, lw), n1 = tile_extent(tile_px, f, k, lh);
-	CHECK(codec_prepare(S, C, CODEC_VAE_DEC, n0, n1, P));
+	CHECK(codec_prepare(S, C, CODEC_VAE_DEC, n0, n1, 1, P));
 	CHECK(run_tiled(S, latent_dev, lw, lh, 4, image_dev, 3, n0, n1, k, f, 1, 1, 0));
 	int64_t n = (int64_t)lw * f * lh * f * 3;
 	ggml_b200_affine(image_dev, image_dev, 1, 0.5f, 0, n);   /* (x+1)/2: [-1,1] -> [0,1] (vae.h:43-47) */
+	return 1;
+}
+
+/* Untiled decode of nb latents in ONE graph run: the images of a batch are independent, so the decoder is
+ * built with a batch dimension -- the 64x64 / 128x128 levels get GEMM rows from all images and every launch is shared.
+ * Returns 0 (nothing done) when the requested tile size makes the decode tiled: the caller then decodes image by image
+ * in the reference's tile order. */
+int sdvae_decode_batch(CodecState* S, MLCtx* C, const VaeParams* P, const float* latent_dev, int lw, int lh, int nb, float* image_dev, int tile_px)
+{
+	const int f = P->f_down, k = 8;
+	if (tile_extent(tile_px, f, k, lw) != lw || tile_extent(tile_px, f, k, lh) != lh || nb < 2) return 0;
+	CHECK(codec_prepare(S, C, CODEC_VAE_DEC, lw, lh, nb, P));
+	const size_t n_in = (size_t)lw * lh * 4 * nb, n_out = (size_t)lw * f * lh * f * 3 * nb;
+	ggml_b200_copy(S->t_in->data, latent_dev, n_in * sizeof(float));   /* same [w,h,c,n] layout */
+	CHECK(mlctx_compute(C));
+	ggml_b200_copy(image_dev, S->t_out->data, n_out * sizeof(float));
+	ggml_b200_affine(image_dev, image_dev, 1, 0.5f, 0, (int64_t)n_out);   /* (x+1)/2: [-1,1] -> [0,1] (vae.h:43-47) */
 	return 1;
 }
 
@@ -219,20 +236,20 @@ int sdvae_encode(CodecState* S, MLCtx* C, const VaeParams* P, const float* image
 	const int f = P->f_down, k = f * 8;
 	if (w % f || h % f) FAIL(-1, "invalid input image size %dx%d", w, h);
 	int n0 = tile_extent(tile_px, 1, k, w), n1 = tile_extent(tile_px, 1, k, h);
-	CHECK(codec_prepare(S, C, CODEC_VAE_ENC, n0, n1, P));
+	CHECK(codec_prepare(S, C, CODEC_VAE_ENC, n0, n1, 1, P));
 	/* [0,1] -> [-1,1] on the tile (vae.h:36-41), then encode */
 	return run_tiled(S, image_dev, w, h, 3, moments_dev, 8, n0, n1, k, 1, f, 2, -1);
 }
 
 int sdtae_decode(CodecState* S, MLCtx* C, const SdTaeParams* P, const float* latent_dev, int lw, int lh, float* image_dev)
 {
-	CHECK(codec_prepare(S, C, CODEC_TAE_DEC, lw, lh, P));
+	CHECK(codec_prepare(S, C, CODEC_TAE_DEC, lw, lh, 1, P));
 	return run_tiled(S, latent_dev, lw, lh, 4, image_dev, 3, lw, lh, 0, 8, 1, 1, 0);   /* output already in [0,1] */
 }
 
 int sdtae_encode(CodecState* S, MLCtx* C, const SdTaeParams* P, const float* image_dev, int w, int h, float* latent_dev)
 {
 	if (w % 8 || h % 8) FAIL(-1, "invalid input image size %dx%d", w, h);
-	CHECK(codec_prepare(S, C, CODEC_TAE_ENC, w, h, P));
+	CHECK(codec_prepare(S, C, CODEC_TAE_ENC, w, h, 1, P));
 	return run_tiled(S, image_dev, w, h, 3, latent_dev, 4, w, h, 0, 1, 8, 1, 0);
 }

@@ -15,12 +15,14 @@ MLTensor* mlb_sdtae_encoder(MLCtx* C, MLTensor* x, const SdTaeParams* P);
 MLTensor* mlb_sdtae_decoder(MLCtx* C, MLTensor* x, const SdTaeParams* P);
 
 /* One cached codec graph (input tile shape -> output tile shape). */
-typedef struct CodecState { MLCtx* ctx; int kind, n0, n1; MLTensor *t_in, *t_out; } CodecState;
+typedef struct CodecState { MLCtx* ctx; int kind, n0, n1, nb; MLTensor *t_in, *t_out; } CodecState;
 enum { CODEC_VAE_DEC = 1, CODEC_VAE_ENC = 2, CODEC_TAE_DEC = 3, CODEC_TAE_ENC = 4 };
 
 /* latent_dev [lw,lh,4] (device f32, SD-scaled) -> image_dev [8lw,8lh,3] (device f32, in [0,1]).
  * tile_px > 0 decodes overlapping tiles in the reference's order and geometry (vae.c:318-410). */
 int sdvae_decode(CodecState* S, MLCtx* C, const VaeParams* P, const float* latent_dev, int lw, int lh, float* image_dev, int tile_px);
+/* nb latents [lw,lh,4,nb] -> images [8lw,8lh,3,nb] in one run of a batched decoder graph; returns 0 if tile_px asks for tiling */
+int sdvae_decode_batch(CodecState* S, MLCtx* C, const VaeParams* P, const float* latent_dev, int lw, int lh, int nb, float* image_dev, int tile_px);
 /* image_dev [w,h,3] in [0,1] -> moments_dev [w/8,h/8,8] (mean | logvar), tiled like vae.c:222-316 */
 int sdvae_encode(CodecState* S, MLCtx* C, const VaeParams* P, const float* image_dev, int w, int h, float* moments_dev, int tile_px);
 int sdtae_decode(CodecState* S, MLCtx* C, const SdTaeParams* P, const float* latent_dev, int lw, int lh, float* image_dev);
