@@ -92,6 +92,38 @@ struct VecCopy {
 	int f[4];                  // src index divisor per iteration dim
 	long long total;
 };
+// Exact unsigned 32-bit division by an invariant divisor (Granlund-Montgomery): q = (t + ((n - t) >> s1)) >> s2 with
+// t = umulhi(n, m). The index decomposition of the copy kernels would otherwise spend several hundred instructions per
+// 16-byte vector on 64-bit divisions and be instruction-bound at ~2.8 TB/s.
+struct FastDiv32 { unsigned m, s1, s2; };
+static FastDiv32 fastdiv32(unsigned d)
+{
+	unsigned l = 0; while ((1ull << l) < d) ++l;
+	FastDiv32 f; f.m = (unsigned)((((1ull << 32) * ((1ull << l) - d)) / d) + 1); f.s1 = l < 1 ? l : 1; f.s2 = l < 1 ? 0 : l - 1;
+	return f;
+}
+__device__ __forceinline__ unsigned fd_div(unsigned n, const FastDiv32& f) { const unsigned t = __umulhi(n, f.m); return (t + ((n - t) >> f.s1)) >> f.s2; }
+
+struct VecCopy32 {
+	const uint4* src; uint4* dst;
+	unsigned n[3]; FastDiv32 dn[3];      // extents of the three fastest iteration dims and their reciprocals
+	long long ds[4], ss[4];
+	unsigned fs[4];                       // log2 of the src index divisor (nearest upscale by 1 or 2)
+	unsigned total;
+};
+__global__ void __launch_bounds__(256)
+vec_copy32_kernel(VecCopy32 c)
+{
+	const unsigned stride = gridDim.x * blockDim.x;
+	for (unsigned lin = blockIdx.x * blockDim.x + threadIdx.x; lin < c.total; lin += stride) {
+		const unsigned r1 = fd_div(lin, c.dn[0]), i0 = lin - r1 * c.n[0];
+		const unsigned r2 = fd_div(r1, c.dn[1]), i1 = r1 - r2 * c.n[1];
+		const unsigned i3 = fd_div(r2, c.dn[2]), i2 = r2 - i3 * c.n[2];
+		c.dst[i0 * c.ds[0] + i1 * c.ds[1] + i2 * c.ds[2] + i3 * c.ds[3]] =
+			__ldg(c.src + i0 * c.ss[0] + (i1 >> c.fs[1]) * c.ss[1] + (i2 >> c.fs[2]) * c.ss[2] + (i3 >> c.fs[3]) * c.ss[3]);
+	}
+}
+
 __global__ void vec_copy_kernel(VecCopy c)
 {
 	for (long long lin = blockIdx.x * (long long)blockDim.x + threadIdx.x; lin < c.total; lin += (long long)gridDim.x * blockDim.x) {
@@ -130,6 +162,18 @@ static bool try_vec_copy(cudaStream_t s, const View& dst, const View& src)
 		c.total *= c.n[j];
 	}
 	if (!c.total) return true;
+	bool pow2 = true;
+	for (int j = 1; j < 4; ++j) pow2 = pow2 && (c.f[j] == 1 || c.f[j] == 2 || c.f[j] == 4);
+	if (pow2 && c.total < 0xffffffffLL) {
+		VecCopy32 q; q.src = c.src; q.dst = c.dst; q.total = (unsigned)c.total;
+		for (int j = 0; j < 3; ++j) { q.n[j] = (unsigned)c.n[j]; q.dn[j] = fastdiv32((unsigned)c.n[j]); }
+		for (int j = 0; j < 4; ++j) { q.ds[j] = c.ds[j]; q.ss[j] = c.ss[j]; q.fs[j] = c.f[j] == 4 ? 2u : c.f[j] == 2 ? 1u : 0u; }
+		// four vectors per thread in flight at most: a grid of a few waves walks the tensor with a grid stride
+		const long long blocks = std::min<long long>((c.total + 255) / 256, 148LL * 8 * 4);
+		vec_copy32_kernel<<<(unsigned)blocks, 256, 0, s>>>(q);
+		g_stats.kernel_launches++;
+		return true;
+	}
 	vec_copy_kernel<<<grid_for(c.total, 256, 2), 256, 0, s>>>(c);
 	g_stats.kernel_launches++;
 	return true;
