@@ -50,6 +50,7 @@ struct AttnTC {
 	AttnParams p;
 	dim3 grid;
 	size_t smem;
+	bool kv1 = false;     // single key block: attn_kv1_kernel
 };
 
 __device__ __forceinline__ float ex2_approx(float x)
@@ -354,6 +355,201 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 	if (warp == W_MMA) { tc_fence_after(); tmem_dealloc(tmem_base, A_TMEM_COLS); }
 }
 
+
+// ------------------------------------------------------------------ single key block (cross-attention, nk <= 128)
+// The text context of a cross-attention has 77 keys (unet.c:110-145): one key block. With one (pair of) query tile(s)
+// per CTA such a launch is a chain of latencies -- load, QK^T, softmax, PV, store -- that nothing overlaps, ~6 us per
+// CTA and 14 waves for the 64x64 level. Here a CTA keeps K and V of its (head, image) in shared memory and WALKS the
+// query tiles: tile i uses slot i & 1 (its own Q buffer, score / output columns in tensor memory and softmax warp
+// group), so the load, the two products and the softmax + store of consecutive tiles overlap.
+//   warp 8  TMA producer: K, V once; Q tiles as their slot's buffer frees up (q_empty)
+//   warp 9  MMA issuer: S_t = Q_t K^T (N = keys rounded up to 16), O_t = P_t V
+//   warps 0..3 / 4..7  slot a / b: one query row per thread -- maximum, exponentials, P (f16, over the consumed scores),
+//           then O / l -> f16 -> global memory, and the slot's accumulator is handed back (o_free).
+template <int D16MAX>
+__global__ void __launch_bounds__(320, 1)
+attn_kv1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+	const AttnParams p)
+{
+	extern __shared__ __align__(1024) uint8_t smem_raw[];
+	uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+	const int tile_bytes = p.dchunks * CHUNK_BYTES;
+	uint8_t* sQ = smem;                       // [2 slots]
+	uint8_t* sK = sQ + 2 * tile_bytes;
+	uint8_t* sV = sK + tile_bytes;
+	uint64_t* bars = (uint64_t*)(sV + tile_bytes);
+	uint64_t* kv_full = bars;                 // [1]
+	uint64_t* q_full = kv_full + 1;           // [2]
+	uint64_t* q_empty = q_full + 2;           // [2]
+	uint64_t* s_full = q_empty + 2;           // [2]
+	uint64_t* p_full = s_full + 2;            // [2]  128 arrivals
+	uint64_t* pv_full = p_full + 2;           // [2]
+	uint64_t* o_free = pv_full + 2;           // [2]  one arrival per warp of the slot
+	uint32_t* tmem_slot = (uint32_t*)(o_free + 2);
+
+	const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
+	const int h = blockIdx.y, b = blockIdx.z;
+	const int n_tiles = (p.nq + AQ - 1) / AQ;
+	const int n_my = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;   // tiles blockIdx.x, + gridDim.x, ...
+	constexpr uint32_t O_BASE = 256, O_STRIDE = 128;      // TMEM: S_t at t*128 (P_t over its first columns), O_t at 256 + t*128
+
+	if (threadIdx.x == 0) {
+		tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+		mbar_init(kv_full, 1);
+		for (int t = 0; t < 2; ++t) { mbar_init(&q_full[t], 1); mbar_init(&q_empty[t], 1); mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 128);
+			mbar_init(&pv_full[t], 1); mbar_init(&o_free[t], 4); }
+		fence_barrier_init();
+	}
+	if (warp == 9) tmem_alloc(tmem_slot, A_TMEM_COLS);
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = uniform_u32(*tmem_slot);
+	const int nk16 = (p.nk + 15) & ~15;                   // keys the products cover (rows past nk are zero-filled by TMA)
+
+	if (warp == 8) {
+		if (lane == 0 && n_my > 0) {
+			mbar_expect_tx(kv_full, 2 * tile_bytes);
+			for (int c = 0; c < p.dchunks; ++c) tma_load_4d(sK + c * CHUNK_BYTES, &tmK, kv_full, c * ACH, 0, h, b);
+			for (int c = 0; c < p.dchunks; ++c) tma_load_4d(sV + c * CHUNK_BYTES, &tmV, kv_full, c * ACH, 0, h, b);
+			for (int i = 0; i < n_my; ++i) {
+				const int t = i & 1, n = i >> 1;
+				if (n > 0) mbar_wait(&q_empty[t], (uint32_t)(n - 1) & 1);
+				mbar_expect_tx(&q_full[t], tile_bytes);
+				const int q0 = ((int)blockIdx.x + i * (int)gridDim.x) * AQ;
+				for (int c = 0; c < p.dchunks; ++c) tma_load_4d(sQ + t * tile_bytes + c * CHUNK_BYTES, &tmQ, &q_full[t], c * ACH, q0, h, b);
+			}
+		}
+	} else if (warp == 9) {
+		const uint32_t idesc_qk = make_idesc_f16(AQ, nk16, 0, 0);
+		const uint32_t idesc_pv = make_idesc_f16(AQ, p.d16, 0, 1);
+		const uint64_t qdesc0 = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+		const uint64_t kdesc0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+		const uint64_t vdesc0 = make_smem_desc_sw128(smem_u32(sV), CHUNK_BYTES, 1024);
+		const uint32_t tile16 = (uint32_t)tile_bytes >> 4;
+		const int nd16 = p.d16 >> 4, nkk = nk16 >> 4;
+		auto issue_qk = [&](int i) {
+			const int t = i & 1, n = i >> 1;
+			mbar_wait(&q_full[t], (uint32_t)n & 1);
+			tc_fence_after();
+			if (elect_one()) {
+				const uint64_t ad = qdesc0 + (uint64_t)(t * tile16);
+				const uint32_t td = tmem_base + t * 128;
+				#pragma unroll
+				for (int kk = 0; kk < D16MAX / 16; ++kk) {
+					const uint32_t off = (uint32_t)((kk >> 2) * (CHUNK_BYTES >> 4) + (kk & 3) * 2);
+					if (kk < nd16) umma_f16(td, ad + off, kdesc0 + off, idesc_qk, kk ? 1u : 0u);
+				}
+				umma_commit(&s_full[t]);
+				umma_commit(&q_empty[t]);
+			}
+			__syncwarp();
+		};
+		auto issue_pv = [&](int i) {
+			const int t = i & 1, n = i >> 1;
+			mbar_wait(&p_full[t], (uint32_t)n & 1);
+			if (n > 0) mbar_wait(&o_free[t], (uint32_t)(n - 1) & 1);      // the slot's previous output has been read
+			tc_fence_after();
+			if (elect_one()) {
+				const uint32_t td = tmem_base + O_BASE + t * O_STRIDE, ta = tmem_base + t * 128;
+				#pragma unroll
+				for (int kk = 0; kk < AK / 16; ++kk)
+					if (kk < nkk) umma_f16_ts(td, ta + kk * 8, vdesc0 + (uint64_t)(kk * 128), idesc_pv, kk ? 1u : 0u);
+				umma_commit(&pv_full[t]);
+			}
+			__syncwarp();
+		};
+		if (n_my > 0) {
+			mbar_wait(kv_full, 0);
+			issue_qk(0);
+			if (n_my > 1) issue_qk(1);
+			for (int i = 0; i < n_my; ++i) {
+				issue_pv(i);                                   // in order after it, S_t / P_t may be overwritten
+				if (i + 2 < n_my) issue_qk(i + 2);
+			}
+		}
+	} else {
+		const int t = warp >> 2, quarter = warp & 3;
+		const int r = quarter * 32 + lane;
+		const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+		const uint32_t ts = tmem_base + t * 128 + lane_off;
+		const uint32_t to = tmem_base + O_BASE + t * O_STRIDE + lane_off;
+		const float sl2 = p.scale_log2;
+		const int nch = (p.nk + 31) >> 5;                     // 32-column chunks holding valid keys
+		for (int n = 0; 2 * n + t < n_my; ++n) {
+			const int i = 2 * n + t;
+			mbar_wait(&s_full[t], (uint32_t)n & 1);
+			tc_fence_after();
+			uint32_t v[32];
+			float mx = -INFINITY;
+			for (int c = 0; c < nch; ++c) {
+				tmem_ld32(ts + c * 32, v);
+				tmem_ld_wait();
+				#pragma unroll
+				for (int k = 0; k < 32; ++k) if (c * 32 + k < p.nk) mx = fmaxf(mx, __uint_as_float(v[k]));
+			}
+			const float mneg = -mx * sl2;
+			float l = 0.f;
+			for (int c = 0; c < nch; ++c) {
+				tmem_ld32(ts + c * 32, v);
+				tmem_ld_wait();
+				uint32_t packed[16];
+				#pragma unroll
+				for (int k = 0; k < 32; k += 2) {
+					float p0 = ex2_approx(fmaf(__uint_as_float(v[k]), sl2, mneg)), p1 = ex2_approx(fmaf(__uint_as_float(v[k + 1]), sl2, mneg));
+					if (c * 32 + k >= p.nk) p0 = 0.f;
+					if (c * 32 + k + 1 >= p.nk) p1 = 0.f;
+					l += p0 + p1;
+					__half2 hh = __floats2half2_rn(p0, p1);
+					packed[k >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+				}
+				tmem_st16(ts + c * 16, packed);               // columns [16c, 16c+16) lie inside scores that were already read
+			}
+			tmem_st_wait();
+			tc_fence_before();
+			mbar_arrive(&p_full[t]);
+
+			mbar_wait(&pv_full[t], (uint32_t)n & 1);
+			tc_fence_after();
+			const long long tok = ((long long)blockIdx.x + (long long)i * gridDim.x) * AQ + r;
+			const float inv = l > 0.f ? 1.0f / l : 0.f;
+			__half* op = (__half*)p.o + tok * p.so_t + (long long)h * p.so_h + (long long)b * p.so_b;
+			const bool vec = ((((uintptr_t)op) & 15) == 0);
+			#pragma unroll
+			for (int c0 = 0; c0 < D16MAX; c0 += 16) {
+				if (c0 < p.d16) {
+					uint32_t o[16];
+					tmem_ld16(to + c0, o);
+					tmem_ld_wait();
+					if (tok < p.nq) {
+						#pragma unroll
+						for (int h8 = 0; h8 < 16; h8 += 8) {
+							const int cc = c0 + h8;
+							if (cc < p.d) {
+								if (vec && cc + 8 <= p.d) {
+									uint4 o4; __half2* hp = reinterpret_cast<__half2*>(&o4);
+									#pragma unroll
+									for (int q = 0; q < 4; ++q) hp[q] = __floats2half2_rn(__uint_as_float(o[h8 + 2 * q]) * inv, __uint_as_float(o[h8 + 2 * q + 1]) * inv);
+									*reinterpret_cast<uint4*>(op + cc) = o4;
+								} else {
+									#pragma unroll
+									for (int q = 0; q < 8; ++q) if (cc + q < p.d) op[cc + q] = __float2half_rn(__uint_as_float(o[h8 + q]) * inv);
+								}
+							}
+						}
+					}
+				}
+			}
+			tc_fence_before();
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&o_free[t]);
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 9) { tc_fence_after(); tmem_dealloc(tmem_base, A_TMEM_COLS); }
+}
+
 // ------------------------------------------------------------------ host
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
 	const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -412,6 +608,20 @@ AttnTC* attn_tc_prepare(const View& o, const View& q, const View& k, const View&
 	while (total() > 220 * 1024 && p.stages > 1) p.stages--;
 	a->smem = total();
 	a->grid = dim3((unsigned)((p.nq + nt * AQ - 1) / (nt * AQ)), (unsigned)p.H, (unsigned)p.B);
+	{
+		// one key block (cross-attention): CTAs walk the query tiles of their (head, image); as many CTAs per (head, image)
+		// as fit the chip in one wave
+		const char* e = getenv("GGML_B200_ATTN_KV1");
+		if (p.nblk == 1 && p.d16 <= 128 && !(e && atoi(e) == 0)) {
+			const int n_tiles = (p.nq + AQ - 1) / AQ;
+			const long long hb = (long long)p.H * p.B;
+			int x = (int)std::max<long long>(1, 148 / std::max<long long>(1, hb));
+			x = std::min(x, n_tiles);
+			a->kv1 = true;
+			a->grid = dim3((unsigned)x, (unsigned)p.H, (unsigned)p.B);
+			a->smem = tile * 4 + 1024 + 512;
+		}
+	}
 	bool ok = encode4(&a->tmQ, q.ptr, p.d, p.nq, p.H, p.B, q.st[1], q.st[2], q.st[3]) &&
 	          encode4(&a->tmK, k.ptr, p.d, p.nk, p.H, p.B, k.st[1], k.st[2], k.st[3]) &&
 	          encode4(&a->tmV, v.ptr, p.d, p.nk, p.H, p.B, v.st[0], v.st[2], v.st[3]);   // v is the [nk, d, H, B] view: token stride = st[0]
@@ -426,7 +636,15 @@ void attn_tc_launch(cudaStream_t s, AttnTC* a)
 		CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<160, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute(attn_kv1_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute(attn_kv1_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		attr_set = true;
+	}
+	if (a->kv1) {
+		if (a->p.d16 <= 64) attn_kv1_kernel<64><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+		else attn_kv1_kernel<128><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+		g_stats.kernel_launches++;
+		return;
 	}
 	if (a->p.d16 <= 64) attn_tc_kernel<64, 2><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
 	else if (a->p.d16 <= 128) attn_tc_kernel<128, 2><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
