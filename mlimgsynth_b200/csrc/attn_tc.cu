@@ -35,7 +35,7 @@ constexpr int A_TMEM_COLS = 512;
 constexpr int A_MAX_STAGES = 4;
 
 struct AttnParams {
-	int d, d16, dchunks, nq, nk, H, B, stages, nblk, pingpong;
+	int d, d16, dchunks, nq, nk, H, B, stages, nblk, pingpong, sep_p;
 	float scale_log2;
 	void* o; long long so_t, so_h, so_b;
 	long long* trace;     // debug timeline (tools/attn_trace.cu); null in production
@@ -98,18 +98,24 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 	uint64_t* s_full = v_empty + A_MAX_STAGES;      // [2 tiles]  QK done
 	uint64_t* p_full = s_full + 2;                  // [2 tiles]  probabilities written (128 arrivals)
 	uint64_t* pv_full = p_full + 2;                 // [2 tiles]  PV done
-	uint32_t* tmem_slot = (uint32_t*)(pv_full + 2);
+	uint64_t* s_free = pv_full + 2;                 // [2 tiles]  scores of the block are in registers (one arrival per softmax warp)
+	uint32_t* tmem_slot = (uint32_t*)(s_free + 2);
 
 	const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
 	const int q0 = blockIdx.x * (NT * AQ), h = blockIdx.y, b = blockIdx.z;
 	const int ntile = (NT == 2 && q0 + AQ < p.nq) ? 2 : 1;     // the second tile may be entirely out of range
-	constexpr uint32_t O_BASE = NT * 128;                      // TMEM: S_t at t*128 (P_t aliases its first 64 columns), O_t behind them
-	constexpr uint32_t O_STRIDE = NT == 2 ? 128 : 256;
+	// TMEM columns: S_t at t*128, O_t behind them, then -- if there is room -- P_t (64 columns of packed f16 pairs);
+	// otherwise P_t aliases the first 64 columns of S_t.
+	constexpr bool SEP_ROOM = NT == 1 || D16MAX <= 64;
+	const bool sep_p = SEP_ROOM && p.sep_p;
+	constexpr uint32_t O_BASE = NT * 128;
+	constexpr uint32_t O_STRIDE = NT == 2 ? (SEP_ROOM ? 64 : 128) : 256;
+	const uint32_t P_BASE = sep_p ? 384 : 0, P_STRIDE = sep_p ? 64 : 128;
 
 	if (threadIdx.x == 0) {
 		tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
 		for (int s = 0; s < p.stages; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-		for (int t = 0; t < 2; ++t) { mbar_init(&q_full[t], 1); mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 128); mbar_init(&pv_full[t], 1); }
+		for (int t = 0; t < 2; ++t) { mbar_init(&q_full[t], 1); mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 128); mbar_init(&pv_full[t], 1); mbar_init(&s_free[t], 4); }
 		fence_barrier_init();
 	}
 	constexpr int W_TMA = NT * 4, W_MMA = NT * 4 + 1;     // the issuing warps have the HIGHEST warp ids: the SM's arbiter favours them
@@ -177,7 +183,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 				// V tile: rows = keys (128 B each), 8-row swizzle atoms 1024 B apart (SBO), next 64 d-columns CHUNK_BYTES
 				// away (LBO); 16 keys further = +16*128 B. P in tensor memory: 16 keys = 8 packed 32-bit columns.
 				const uint64_t bd = vdesc0 + (uint64_t)(s * tile16);
-				const uint32_t td = tmem_base + O_BASE + t * O_STRIDE, ta = tmem_base + t * 128;
+				const uint32_t td = tmem_base + O_BASE + t * O_STRIDE, ta = tmem_base + P_BASE + t * P_STRIDE;
 				const int nkk = (min(AK, p.nk - j * AK) + 15) >> 4;
 				#pragma unroll
 				for (int kk = 0; kk < AK / 16; ++kk)
@@ -192,8 +198,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 		for (int t = 0; t < ntile; ++t) issue_qk(t, 0);
 		for (int j = 0; j < p.nblk; ++j) {
 			for (int t = 0; t < ntile; ++t) {
-				issue_pv(t, j);                             // in-order after it: S_t/P_t may be overwritten
-				if (j + 1 < p.nblk) issue_qk(t, j + 1);
+				if (sep_p) {
+					// S_t is free once the softmax warps hold block j's scores in registers: the next QK^T goes first
+					if (j + 1 < p.nblk) { mbar_wait(&s_free[t], (uint32_t)j & 1); issue_qk(t, j + 1); }
+					issue_pv(t, j);
+				} else {
+					issue_pv(t, j);                             // in-order after it: S_t/P_t may be overwritten
+					if (j + 1 < p.nblk) issue_qk(t, j + 1);
+				}
 			}
 		}
 	} else {
@@ -203,7 +215,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 			const int quarter = warp & 3;
 			const int r = quarter * 32 + lane;
 			const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-			const uint32_t ts = tmem_base + t * 128 + lane_off;                     // scores / probabilities of this row
+			const uint32_t ts = tmem_base + t * 128 + lane_off;                     // scores of this row
+			const uint32_t tp = tmem_base + P_BASE + t * P_STRIDE + lane_off;        // probabilities of this row (packed f16 pairs)
 			const uint32_t to = tmem_base + O_BASE + t * O_STRIDE + lane_off;       // output accumulator of this row
 			const float sl2 = p.scale_log2;
 			float m = -INFINITY, l = 0.f;     // running (possibly stale) maximum in the exp2 domain, running sum
@@ -275,6 +288,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 				if (tr) ATTN_TR(t, j, 2);
 				if (pingpong) named_bar_sync(2 + t, 256);
 				if (tr) ATTN_TR(t, j, 3);
+				// separate P columns: the previous block's PV product must have consumed P_t before it is rewritten
+				if (sep_p && j > 0) { mbar_wait(&pv_full[t], (uint32_t)(j - 1) & 1); tc_fence_after(); }
 				const float mneg = -m;
 				// Exp pass, software-pipelined over the four 32-column chunks with three register buffers: the
 				// exponentials (FFMA + MUFU.EX2, in place) of chunk c+1 are issued BEFORE the sum / f16 pack /
@@ -297,12 +312,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 						__half2 hh = __floats2half2_rn(p0, p1);
 						packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
 					}
-					tmem_st16(ts + c * 16, packed);    // columns [16c, 16c+16) lie inside scores that were already read
+					tmem_st16(tp + c * 16, packed);    // (aliased layout: columns [16c, 16c+16) lie inside scores that were already read)
 				};
 				tmem_ld_wait(); tmem_ld32(ts + 32, vb); exps(va, 0);
 				tmem_ld_wait(); tmem_ld32(ts + 64, vc); exps(vb, 1); finish(va, 0);
 				tmem_ld_wait(); tmem_ld32(ts + 96, va); exps(vc, 2); finish(vb, 1);
-				tmem_ld_wait();                         exps(va, 3); finish(vc, 2);
+				tmem_ld_wait();
+				if (sep_p) {                            // every score of the block is in registers: S_t may be overwritten
+					tc_fence_before();
+					__syncwarp();
+					if (lane == 0) mbar_arrive(&s_free[t]);
+				}
+				exps(va, 3); finish(vc, 2);
 				finish(va, 3);
 				if (tr) ATTN_TR(t, j, 4);
 				if (pingpong && (t == 0 || j + 1 < p.nblk)) named_bar_arrive(2 + (t ^ 1), 256);
@@ -596,6 +617,7 @@ AttnTC* attn_tc_prepare(const View& o, const View& q, const View& k, const View&
 	AttnParams& p = a->p;
 	p.trace = nullptr;
 	{ const char* e = getenv("GGML_B200_ATTN_PP"); p.pingpong = e ? atoi(e) : 1; }
+	{ const char* e = getenv("GGML_B200_ATTN_SEP"); p.sep_p = e ? atoi(e) : 0; }
 	p.d = (int)q.ne[0]; p.d16 = (p.d + 15) / 16 * 16; p.dchunks = (p.d + ACH - 1) / ACH;
 	p.nq = (int)q.ne[1]; p.nk = (int)k.ne[1]; p.H = (int)q.ne[2]; p.B = (int)q.ne[3];
 	p.nblk = (p.nk + AK - 1) / AK;
