@@ -86,6 +86,10 @@ ggml_backend_t ggml_backend_init_by_name(const char* name, const char* params)
 		return nullptr;
 	}
 	CUDA_CHECK(cudaSetDevice(dev));
+	// The tcgen05 kernels run with the maximum shared-memory carve-out (up to 227 KB per CTA). Give every other kernel the
+	// same preference so that the SMs do not re-partition L1 / shared memory between consecutive kernels of a graph
+	// (the streaming element-wise kernels do not depend on L1 capacity). GGML_B200_CARVEOUT=0 keeps the driver default.
+	{ const char* e = getenv("GGML_B200_CARVEOUT"); if (!(e && atoi(e) == 0)) CUDA_CHECK(cudaDeviceSetCacheConfig(cudaFuncCachePreferShared)); }
 	ggml_backend* b = new ggml_backend();
 	b->be.device = dev;
 	b->be.sm_count = pr.multiProcessorCount;
