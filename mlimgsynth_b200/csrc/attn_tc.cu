@@ -35,7 +35,7 @@ constexpr int A_TMEM_COLS = 512;
 constexpr int A_MAX_STAGES = 4;
 
 struct AttnParams {
-	int d, d16, dchunks, nq, nk, H, B, stages, nblk, pingpong, sep_p;
+	int d, d16, dchunks, nq, nk, H, B, stages, nblk, pingpong, sep_p, dual;
 	float scale_log2;
 	void* o; long long so_t, so_h, so_b;
 	long long* trace;     // debug timeline (tools/attn_trace.cu); null in production
@@ -78,8 +78,12 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 		:: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-template <int D16MAX, int NT>     // NT = query tiles per CTA (2: ping-pong, 320 threads; 1: wide heads, 192 threads)
-__global__ void __launch_bounds__(64 + 128 * NT, 1)
+// NT = query tiles per CTA (2: ping-pong, 320 threads; 1: 192 threads). <64, 1> is the "dual" form: one tile, 256 tensor
+// memory columns and <= 113 KB of shared memory, so that TWO CTAs share an SM -- two softmax warps per SM sub-partition
+// keep the MUFU unit busier than one (8.6 vs 9.6 clk per exponential, tools/pipe_rates.cu) and each CTA's QK/PV latency
+// hides behind the other's exponentials without an explicit ping-pong.
+template <int D16MAX, int NT>
+__global__ void __launch_bounds__(64 + 128 * NT, (NT == 1 && D16MAX <= 64) ? 2 : 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
 	const AttnParams p)
 {
@@ -107,7 +111,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 	// TMEM columns: S_t at t*128, O_t behind them, then -- if there is room -- P_t (64 columns of packed f16 pairs);
 	// otherwise P_t aliases the first 64 columns of S_t.
 	constexpr bool SEP_ROOM = NT == 1 || D16MAX <= 64;
-	const bool sep_p = SEP_ROOM && p.sep_p;
+	const bool sep_p = SEP_ROOM && p.sep_p && !(NT == 1 && D16MAX <= 64);       // (the dual form has no room for separate P columns)
 	constexpr uint32_t O_BASE = NT * 128;
 	constexpr uint32_t O_STRIDE = NT == 2 ? (SEP_ROOM ? 64 : 128) : 256;
 	const uint32_t P_BASE = sep_p ? 384 : 0, P_STRIDE = sep_p ? 64 : 128;
@@ -119,7 +123,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 		fence_barrier_init();
 	}
 	constexpr int W_TMA = NT * 4, W_MMA = NT * 4 + 1;     // the issuing warps have the HIGHEST warp ids: the SM's arbiter favours them
-	if (warp == W_MMA) tmem_alloc(tmem_slot, A_TMEM_COLS);
+	constexpr uint32_t TMEM_COLS_USED = (NT == 1 && D16MAX <= 64) ? 256 : A_TMEM_COLS;
+	if (warp == W_MMA) tmem_alloc(tmem_slot, TMEM_COLS_USED);
 	tc_fence_before();
 	__syncthreads();
 	tc_fence_after();
@@ -373,7 +378,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 	}
 	tc_fence_before();
 	__syncthreads();
-	if (warp == W_MMA) { tc_fence_after(); tmem_dealloc(tmem_base, A_TMEM_COLS); }
+	if (warp == W_MMA) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS_USED); }
 }
 
 
@@ -625,7 +630,10 @@ AttnTC* attn_tc_prepare(const View& o, const View& q, const View& k, const View&
 	p.o = o.ptr; p.so_t = o.st[1]; p.so_h = o.st[2]; p.so_b = o.st[3];
 	const size_t tile = (size_t)p.dchunks * CHUNK_BYTES;
 	p.stages = std::max(1, std::min(p.nblk, A_MAX_STAGES));
-	const int nt = p.d16 > 128 ? 1 : 2;
+	// heads up to 64 wide: one tile per CTA, two CTAs per SM (measured 7-12 % faster than two ping-pong tiles in one CTA)
+	{ const char* e = getenv("GGML_B200_ATTN_DUAL"); p.dual = (e ? atoi(e) : 1) && p.d16 <= 64 && p.nblk > 1; }
+	const int nt = (p.d16 > 128 || p.dual) ? 1 : 2;
+	if (p.dual) p.stages = std::min(p.stages, 2);             // two CTAs per SM: <= 113 KB each
 	auto total = [&]() { return tile * (nt + 2 * p.stages) + 1024 + 512; };
 	while (total() > 220 * 1024 && p.stages > 1) p.stages--;
 	a->smem = total();
@@ -658,6 +666,7 @@ void attn_tc_launch(cudaStream_t s, AttnTC* a)
 		CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<160, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute(attn_kv1_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute(attn_kv1_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		attr_set = true;
@@ -668,7 +677,8 @@ void attn_tc_launch(cudaStream_t s, AttnTC* a)
 		g_stats.kernel_launches++;
 		return;
 	}
-	if (a->p.d16 <= 64) attn_tc_kernel<64, 2><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+	if (a->p.dual) attn_tc_kernel<64, 1><<<a->grid, 192, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+	else if (a->p.d16 <= 64) attn_tc_kernel<64, 2><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
 	else if (a->p.d16 <= 128) attn_tc_kernel<128, 2><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
 	else attn_tc_kernel<160, 1><<<a->grid, 192, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
 	g_stats.kernel_launches++;
