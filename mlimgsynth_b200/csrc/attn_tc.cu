@@ -35,7 +35,7 @@ constexpr int A_TMEM_COLS = 512;
 constexpr int A_MAX_STAGES = 4;
 
 struct AttnParams {
-	int d, d16, dchunks, nq, nk, H, B, stages, nblk, pingpong, sep_p, dual;
+	int d, d16, dchunks, nq, nk, H, B, stages, nblk, pingpong, sep_p, dual, npoly;
 	float scale_log2;
 	void* o; long long so_t, so_h, so_b;
 	long long* trace;     // debug timeline (tools/attn_trace.cu); null in production
@@ -55,6 +55,21 @@ struct AttnTC {
 
 __device__ __forceinline__ float ex2_approx(float x)
 { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// 2^x for x <= ~0 on the FMA / ALU pipes: x = n + f, n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 minimax polynomial
+// (relative error 7.5e-5, below f16 rounding); n is added to the exponent field (the low mantissa bits of x + 1.5 * 2^23).
+__device__ __forceinline__ float ex2_poly(float x)
+{
+	x = fmaxf(x, -126.0f);
+	const float magic = 12582912.0f;
+	const float xr = x + magic;
+	const float n = xr - magic;
+	const float f = x - n;
+	float p = fmaf(f, 0.0551716648f, 0.242611125f);
+	p = fmaf(p, f, 0.693260968f);
+	p = fmaf(p, f, 0.999928057f);
+	return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
+}
 
 __device__ __forceinline__ float max3f(float a, float b, float c)
 { float y; asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c)); return y; }
@@ -82,7 +97,7 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 // memory columns and <= 113 KB of shared memory, so that TWO CTAs share an SM -- two softmax warps per SM sub-partition
 // keep the MUFU unit busier than one (8.6 vs 9.6 clk per exponential, tools/pipe_rates.cu) and each CTA's QK/PV latency
 // hides behind the other's exponentials without an explicit ping-pong.
-template <int D16MAX, int NT>
+template <int D16MAX, int NT, int N_POLY = 0>       // N_POLY of every 8 exponentials run on the FMA pipe instead of the MUFU unit
 __global__ void __launch_bounds__(64 + 128 * NT, (NT == 1 && D16MAX <= 64) ? 2 : 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
 	const AttnParams p)
@@ -303,7 +318,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 				auto exps = [&](uint32_t* v, int c) {
 					#pragma unroll
 					for (int i = 0; i < 32; ++i) {
-						float e = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, mneg));
+						const float xs = fmaf(__uint_as_float(v[i]), sl2, mneg);
+						float e = (i & 7) < N_POLY ? ex2_poly(xs) : ex2_approx(xs);
 						if (!FULL) { if (c * 32 + i >= valid) e = 0.f; }
 						v[i] = __float_as_uint(e);
 					}
@@ -623,6 +639,8 @@ AttnTC* attn_tc_prepare(const View& o, const View& q, const View& k, const View&
 	p.trace = nullptr;
 	{ const char* e = getenv("GGML_B200_ATTN_PP"); p.pingpong = e ? atoi(e) : 1; }
 	{ const char* e = getenv("GGML_B200_ATTN_SEP"); p.sep_p = e ? atoi(e) : 0; }
+	// dual form: one exponential in eight on the FMA pipe (measured -4 % at d = 40, -2.6 % at d = 64; two in eight is worse)
+	{ const char* e = getenv("GGML_B200_ATTN_POLY"); p.npoly = e ? atoi(e) : 1; }
 	p.d = (int)q.ne[0]; p.d16 = (p.d + 15) / 16 * 16; p.dchunks = (p.d + ACH - 1) / ACH;
 	p.nq = (int)q.ne[1]; p.nk = (int)k.ne[1]; p.H = (int)q.ne[2]; p.B = (int)q.ne[3];
 	p.nblk = (p.nk + AK - 1) / AK;
@@ -667,6 +685,8 @@ void attn_tc_launch(cudaStream_t s, AttnTC* a)
 		CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<160, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute((attn_tc_kernel<64, 1, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute((attn_tc_kernel<64, 1, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute(attn_kv1_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute(attn_kv1_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		attr_set = true;
@@ -677,7 +697,9 @@ void attn_tc_launch(cudaStream_t s, AttnTC* a)
 		g_stats.kernel_launches++;
 		return;
 	}
-	if (a->p.dual) attn_tc_kernel<64, 1><<<a->grid, 192, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+	if (a->p.dual && a->p.npoly == 2) attn_tc_kernel<64, 1, 2><<<a->grid, 192, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+	else if (a->p.dual && a->p.npoly == 1) attn_tc_kernel<64, 1, 1><<<a->grid, 192, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+	else if (a->p.dual) attn_tc_kernel<64, 1><<<a->grid, 192, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
 	else if (a->p.d16 <= 64) attn_tc_kernel<64, 2><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
 	else if (a->p.d16 <= 128) attn_tc_kernel<128, 2><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
 	else attn_tc_kernel<160, 1><<<a->grid, 192, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
