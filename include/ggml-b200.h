@@ -73,6 +73,9 @@ GGML_API double ggml_b200_timer_stop(void);
 /* counters: kernels launched by this library, graph replays, bytes moved across PCIe */
 struct ggml_b200_stats { uint64_t kernel_launches, graph_launches, plans_built, h2d_bytes, d2h_bytes; };
 GGML_API const struct ggml_b200_stats* ggml_b200_get_stats(void);
+/* Steps of the most recently planned graph: key = a step kind ("GEMM_TC", "CONV_TC", "ATTENTION", "GROUPNORM", "LAYERNORM",
+ * "COPY", ...), "name:<step name>" (e.g. "name:linear_fused", "name:linear_geglu"), "steps" or "preps" (totals). */
+GGML_API int ggml_b200_last_plan_count(const char* key);
 
 #ifdef __cplusplus
 }

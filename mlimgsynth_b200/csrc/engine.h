@@ -46,6 +46,7 @@ struct Plan;
 struct Backend;
 
 Plan* plan_build(Backend* be, ggml_cgraph* g);
+int last_plan_count(const char* key);      // step histogram of the most recently built plan
 void  plan_run(Plan* p);
 void  plan_free(Plan* p);
 void  profile_enable(bool on);

@@ -1154,14 +1154,22 @@ static void run_step(Plan* P, Step& s, cudaStream_t st)
 	}
 }
 
+// step histogram of the most recently built plan (ggml_b200_last_plan_count): lets the CPU-only tests check what the
+// planner fused, in dry-run mode
+static std::map<std::string, int> g_last_plan_hist;
+int last_plan_count(const char* key) { auto it = g_last_plan_hist.find(key ? key : "steps"); return it == g_last_plan_hist.end() ? 0 : it->second; }
+
 static void dump_plan(Plan* P)
 {
 	static const char* kn[] = { "COPY", "BINARY", "UNARY", "UPSCALE", "SOFTMAX", "GET_ROWS", "TSEMB", "GEMM_SIMT",
 		"GROUPNORM", "LAYERNORM", "GEGLU", "IM2COL", "WPREP_CONV", "ATTENTION", "GEMM_TC", "CONV_TC", "ZERO", "SOFTMAX_F16", "WPREP_GEGLU" };
 	std::map<std::string, int> hist;
 	for (Step& s : P->steps) hist[kn[s.kind]]++;
+	g_last_plan_hist = hist; g_last_plan_hist["steps"] = (int)P->steps.size(); g_last_plan_hist["preps"] = (int)P->prep.size();
+	for (Step& s : P->steps) g_last_plan_hist[std::string("name:") + s.name]++;
 	std::string line;
 	for (auto& kv : hist) line += kv.first + ":" + std::to_string(kv.second) + " ";
+	if (env_flag("GGML_B200_QUIET")) return;      // (the histogram above is always recorded)
 	B200_LOG("plan: %zu nodes -> %zu steps (+%zu weight preps), arena %.1f MiB, prepared weights %.1f MiB | %s",
 		P->graph->nodes.size(), P->steps.size(), P->prep.size(), P->arena_bytes / 1048576.0, P->persist_bytes / 1048576.0, line.c_str());
 	if (env_flag("GGML_B200_DUMP_PLAN")) {
@@ -1194,7 +1202,7 @@ Plan* plan_build(Backend* be, ggml_cgraph* g)
 		if (P->persist_bytes) CUDA_CHECK(cudaMalloc(&P->persist, P->persist_bytes));
 	}
 	g_stats.plans_built++;
-	if (!env_flag("GGML_B200_QUIET")) dump_plan(P);
+	dump_plan(P);
 	return P;
 }
 

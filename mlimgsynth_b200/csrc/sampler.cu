@@ -255,5 +255,6 @@ double ggml_b200_timer_stop(void)
 	return ms;
 }
 const struct ggml_b200_stats* ggml_b200_get_stats(void) { return (const struct ggml_b200_stats*)&g_stats; }
+int ggml_b200_last_plan_count(const char* key) { return b200::last_plan_count(key); }
 
 }  // extern "C"
