@@ -5,7 +5,7 @@ parser, sigma<->t maps of the B200 host layer (libmlimgsynth_b200.so) against
       test_text_tokenize_clip.c:41-66), and
   (2) the reference's prompt-parser test cases (test_prompt_preproc.c:101-127), restated here.
 """
-import ctypes as C, json, os, struct
+import ctypes as C, json, os, struct, sys
 import pytest
 import mlimgsynth_b200
 from mlimgsynth_b200 import api
@@ -135,3 +135,38 @@ def test_option_api_errors():
     with pytest.raises(api.MLISError):   # no model set: fails loudly, no CPU fallback
         c.generate()
     c.close()
+
+
+def test_tensor_name_conversion_matches_reference(oracle_built):
+    """Weight ingestion: every checkpoint key of the SD1.x / SD2.x / SDXL architectures (CLIP HF and OpenCLIP
+    towers, VAE, UNet; 3276 names) plus keys the loader must ignore map through host/name_conv.c exactly as through the
+    reference's tensor_name_conv.c:274 (compiled unmodified into oracle/_ref): same result code (unused / good / fused-QKV)
+    and the same internal name."""
+    import ctypes as C
+    sys.path.insert(0, os.path.join(mlimgsynth_b200.ROOT, "tools"))
+    import gen_weights
+
+    class StrSlice(C.Structure):
+        _fields_ = [("b", C.c_char_p), ("s", C.c_size_t)]
+    ref_lib = os.path.join(oracle_built, "libmlimgsynth_cpu.so")
+    if not os.path.exists(ref_lib):
+        pytest.skip("oracle/_ref/libmlimgsynth_cpu.so not built")
+    R = C.CDLL(ref_lib); R.tnconv_sd.argtypes = [StrSlice, C.POINTER(C.c_void_p)]
+    O = C.CDLL(mlimgsynth_b200.HOST_LIB); O.tnconv_sd.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
+    names = []
+    for kind in ("sd1", "sd2", "sdxl"):
+        names += [n for n, _, _ in gen_weights.build_spec(kind).items]
+    names += ["model_ema.decay", "alphas_cumprod", "cond_stage_model.transformer.text_model.embeddings.position_ids",
+              "first_stage_model.loss.logvar", "foo.bar", "model.diffusion_model.unknown_block.0.weight"]
+    names = list(dict.fromkeys(names))
+    assert len(names) > 3000
+    for n in names:
+        b = n.encode()
+        out = C.c_void_p(None)
+        r = R.tnconv_sd(StrSlice(b, len(b)), C.byref(out))
+        want = C.string_at(out.value).decode() if out.value else ""
+        buf = C.create_string_buffer(512)
+        o = O.tnconv_sd(b, buf, 512)
+        assert (r > 0) == (o > 0), (n, r, o)
+        if r > 0:
+            assert (o, buf.value.decode()) == (r, want), (n, r, want, o, buf.value.decode())
