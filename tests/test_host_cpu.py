@@ -170,3 +170,76 @@ def test_tensor_name_conversion_matches_reference(oracle_built):
         assert (r > 0) == (o > 0), (n, r, o)
         if r > 0:
             assert (o, buf.value.decode()) == (r, want), (n, r, want, o, buf.value.decode())
+
+
+def test_tensor_store_reads_and_converts_safetensors(tmp_path):
+    """Weight ingestion: safetensors index, shape reversal to ggml order (tensorstore_safet.c:138-142), name
+    mapping through the converter, dropped unknown keys, and the dtype conversions the engine asks for: F32 -> F16 rounds to
+    nearest even like ggml_fp32_to_fp16_row, BF16 -> F32 is exact, BF16 -> F16 goes through F32."""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    a32 = (rng.standard_normal((5, 7)) * 3).astype(np.float32)
+    a32[0, :4] = [65504.0, 1e-8, -0.0, 6.1e-5]                       # f16 max, underflow, signed zero, smallest normal region
+    a16 = rng.standard_normal((3, 2, 4)).astype(np.float16)
+    bf_src = rng.standard_normal(11).astype(np.float32)
+    abf = (bf_src.view(np.uint32) >> 16).astype(np.uint16)           # bf16 bit patterns (truncation is fine for a fixture)
+    tensors = [("model.diffusion_model.time_embed.0.weight", "F32", a32.shape, a32.tobytes()),
+               ("model.diffusion_model.time_embed.0.bias", "BF16", abf.shape, abf.tobytes()),
+               ("first_stage_model.post_quant_conv.weight", "F16", a16.shape, a16.tobytes()),
+               ("model_ema.decay", "F32", (1,), np.zeros(1, np.float32).tobytes())]
+    header, off = {}, 0
+    for name, dt, shape, raw in tensors:
+        header[name] = {"dtype": dt, "shape": list(shape), "data_offsets": [off, off + len(raw)]}
+        off += len(raw)
+    hj = json.dumps(header, separators=(",", ":")).encode()
+    hj += b" " * ((8 - len(hj) % 8) % 8)
+    path = str(tmp_path / "mini.safetensors")
+    with open(path, "wb") as f:
+        f.write(struct.pack("<Q", len(hj))); f.write(hj)
+        for _, _, _, raw in tensors:
+            f.write(raw)
+
+    class TSEntry(C.Structure):
+        _fields_ = [("key", C.c_char_p), ("dtype", C.c_int), ("ndim", C.c_int), ("shape", C.c_int64 * 4), ("data", C.c_void_p),
+                    ("nbytes", C.c_size_t), ("owned", C.c_bool)]
+
+    class TStore(C.Structure):
+        _fields_ = [("e", C.POINTER(TSEntry)), ("n", C.c_int), ("cap", C.c_int), ("hash", C.POINTER(C.c_int)), ("hash_cap", C.c_int),
+                    ("map", C.c_void_p), ("map_size", C.c_size_t)]
+    L = C.CDLL(mlimgsynth_b200.HOST_LIB)
+    L.tstore_read_safetensors.argtypes = [C.POINTER(TStore), C.c_char_p, C.c_void_p, C.c_char_p]
+    L.tstore_find.restype = C.POINTER(TSEntry); L.tstore_find.argtypes = [C.POINTER(TStore), C.c_char_p]
+    L.tsentry_as.restype = C.c_void_p; L.tsentry_as.argtypes = [C.POINTER(TSEntry), C.c_int, C.POINTER(C.c_void_p)]
+    L.tsentry_count.restype = C.c_int64; L.tsentry_count.argtypes = [C.POINTER(TSEntry)]
+    conv = C.cast(L.tnconv_sd, C.c_void_p)
+    S = TStore()
+    assert L.tstore_read_safetensors(C.byref(S), path.encode(), conv, None) >= 1
+    assert S.n == 3                                                  # model_ema.decay is not a tensor of the path: dropped
+
+    def fetch(key, want, npdt, count):
+        e = L.tstore_find(C.byref(S), key)
+        assert e, key
+        assert L.tsentry_count(e) == count
+        tofree = C.c_void_p(None)
+        p = L.tsentry_as(e, want, C.byref(tofree))
+        assert p
+        return np.frombuffer(C.string_at(p, count * np.dtype(npdt).itemsize), dtype=npdt).copy(), e.contents
+
+    # names and ggml-order shapes
+    k_w = [k for k in (b"unet.embed.0.weight", b"unet.time_embed.0.weight") if L.tstore_find(C.byref(S), k)]
+    assert k_w, "time_embed weight not mapped"
+    w16, ew = fetch(k_w[0], 1, np.float16, 35)
+    assert list(ew.shape)[:2] == [7, 5] and ew.dtype == 0
+    assert np.array_equal(w16.view(np.uint16), a32.astype(np.float16).reshape(-1).view(np.uint16))       # round to nearest even, bit for bit
+    w32, _ = fetch(k_w[0], 0, np.float32, 35)
+    assert np.array_equal(w32, a32.reshape(-1))
+    k_b = k_w[0].replace(b"weight", b"bias")
+    b32, eb = fetch(k_b, 0, np.float32, 11)
+    assert eb.dtype == 2 and np.array_equal(b32.view(np.uint32), abf.astype(np.uint32) << 16)
+    b16, _ = fetch(k_b, 1, np.float16, 11)
+    assert np.array_equal(b16.view(np.uint16), (abf.astype(np.uint32) << 16).view(np.float32).astype(np.float16).view(np.uint16))
+    k_v = [k for k in (b"vae.post_quant_conv.weight",) if L.tstore_find(C.byref(S), k)]
+    assert k_v
+    v16, ev = fetch(k_v[0], 1, np.float16, 24)
+    assert list(ev.shape)[:3] == [4, 2, 3] and np.array_equal(v16.view(np.uint16), a16.reshape(-1).view(np.uint16))
+    L.tstore_free(C.byref(S))
