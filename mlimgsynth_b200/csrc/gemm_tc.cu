@@ -46,6 +46,15 @@ struct GemmParams {
 	int n_stg;                         // staging tiles (2: the TMA store of tile i drains while tile i+1 is written)
 	long long* trace;                  // debug timeline of CTA 0's epilogue (GGML_B200_GEMM_TRACE), null in production
 	uint32_t mul_nct, mul_tw, mul_th;  // reciprocal multipliers of n_ctiles / tiles_w / tiles_h: tile coordinates without integer division
+	int split_k, kbps;                 // split-K (gemm_tc_kernel only): blockIdx.z covers k-blocks [z * kbps, (z + 1) * kbps) and writes f32 partials
+};
+
+// What the reduction pass of a split-K launch needs: the real output and the epilogue that the GEMM kernel skipped.
+struct SplitK {
+	int S = 1; float* ws = nullptr;
+	void* C = nullptr; long long ldc = 0;
+	const float* bias = nullptr; const void* rowvec = nullptr; int rowvec_dt = 0; long long rowvec_stride = 0, rows_per_image = 1;
+	const void* residual = nullptr; long long ldr = 0; int act = 0;
 };
 
 // q = n / d through one multiply-high: mul = ceil(2^32 / d) is exact while n * d < 2^32 (tile counts are far below); d == 1 has mul == 0
@@ -58,6 +67,7 @@ struct GemmTC {
 	dim3 grid;
 	size_t smem;
 	bool persistent = false;
+	SplitK sk;
 };
 
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row swizzle atoms 1024 B apart.
@@ -133,13 +143,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 	tc_fence_after();
 	const uint32_t tmem_base = *tmem_slot;
 
+	// split-K: this CTA covers k-blocks [kb0, kb1) and writes its f32 partial sums to slice blockIdx.z of the workspace
+	const int kb0 = p.split_k > 1 ? (int)blockIdx.z * p.kbps : 0, kb1 = p.split_k > 1 ? min(p.num_kb, kb0 + p.kbps) : p.num_kb;
 	if (warp == 0) {
 		// ===== TMA producer =====
 		if (lane == 0) {
 			const int cpt = p.conv ? p.Cin / BK : 1;  // channel chunks per tap
-			for (int kb = 0; kb < p.num_kb; ++kb) {
-				const int s = kb % p.stages;
-				const uint32_t ph = (uint32_t)(kb / p.stages) & 1;
+			for (int kb = kb0; kb < kb1; ++kb) {
+				const int s = (kb - kb0) % p.stages;
+				const uint32_t ph = (uint32_t)((kb - kb0) / p.stages) & 1;
 				mbar_wait(&empty_bar[s], ph ^ 1);
 				uint8_t* sa = smem + (size_t)s * stage_bytes;
 				uint8_t* sb = sa + a_bytes;
@@ -158,9 +170,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 		// ===== MMA issuer (one thread) =====
 		if (lane == 0) {
 			const uint32_t idesc = make_idesc(p.BN);
-			for (int kb = 0; kb < p.num_kb; ++kb) {
-				const int s = kb % p.stages;
-				const uint32_t ph = (uint32_t)(kb / p.stages) & 1;
+			for (int kb = kb0; kb < kb1; ++kb) {
+				const int s = (kb - kb0) % p.stages;
+				const uint32_t ph = (uint32_t)((kb - kb0) / p.stages) & 1;
 				mbar_wait(&full_bar[s], ph);
 				tc_fence_after();
 				const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
@@ -168,7 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 				#pragma unroll
 				for (int k = 0; k < BK / 16; ++k) {
 					// advance 16 elements (32 B) along K inside the swizzle row: +2 in 16-byte units
-					umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+					umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) ? 1u : 0u);
 				}
 				umma_commit(&empty_bar[s]);          // slot reusable once these MMAs retire
 			}
@@ -273,7 +285,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 					for (int j = 0; j < 16; ++j) if (full || col0 + j < p.N) f[j] += rp[j];
 				}
 			}
-			const long long co = grow * p.ldc + col0;
+			const long long co = grow * p.ldc + col0 + (p.split_k > 1 ? (long long)blockIdx.z * p.M * p.ldc : 0);
 			if (p.c_dt == DT_F16) {
 				__half* cp = (__half*)p.C + co;
 				if (full && ((co & 7) == 0)) {
@@ -719,6 +731,41 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 	if (warp == 9) { tc_fence_after(); if (TWO_SM) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
+// ------------------------------------------------------------------ split-K reduction + epilogue
+// out[row, col] = act(sum_s ws[s][row][col] + bias[col] + rowvec[image(row)][col]) + residual[row, col]   (f16, 4 columns per thread)
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, int S, long long M, int N, __half* __restrict__ C, long long ldc,
+	const float* __restrict__ bias, const void* __restrict__ rowvec, int rowvec_dt, long long rowvec_stride, long long rows_per_image,
+	int act, const __half* __restrict__ residual, long long ldr)
+{
+	const int n4 = N >> 2;
+	const long long total = M * n4, slice = M * (long long)N;
+	for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+		const long long row = idx / n4; const int col = (int)(idx - row * n4) * 4;
+		const float* src = ws + row * N + col;
+		float4 a = *reinterpret_cast<const float4*>(src);
+		for (int sidx = 1; sidx < S; ++sidx) { const float4 b = *reinterpret_cast<const float4*>(src + sidx * slice); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+		float f[4] = { a.x, a.y, a.z, a.w };
+		if (bias) { const float4 b = *reinterpret_cast<const float4*>(bias + col); f[0] += b.x; f[1] += b.y; f[2] += b.z; f[3] += b.w; }
+		if (rowvec) {
+			const long long o = (row / rows_per_image) * rowvec_stride + col;
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) f[j] += rowvec_dt == DT_F16 ? __half2float(((const __half*)rowvec)[o + j]) : ((const float*)rowvec)[o + j];
+		}
+		if (act != U_NONE) {
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) f[j] = act_apply_tc(act, f[j]);
+		}
+		if (residual) {
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) f[j] += __half2float(residual[row * ldr + col + j]);
+		}
+		__half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
+		__half* dst = C + row * ldc + col;
+		*reinterpret_cast<__half2*>(dst) = h0; *reinterpret_cast<__half2*>(dst + 2) = h1;
+	}
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
 	const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -788,6 +835,46 @@ static void finish_setup(GemmTC* g, const GemmEpilogue& ep, int64_t m_tiles, int
 
 // ---- persistent kernel setup
 static bool env_on(const char* n, bool dflt) { const char* e = getenv(n); return e && *e ? atoi(e) != 0 : dflt; }
+
+// Split-K for contractions with few output tiles and a long K (the 8x8-level convolutions of SD1.x: M = 1024, N = 1280,
+// K = 11520 / 23040): with 40-112 tiles every CTA has to pull 5+ MB of operands through its own L2 port and the launch is
+// ingest-bound at ~590 TFLOP/s. Here 128 x 256 tiles are cut along K so that about one CTA per SM works on 1/S of it,
+// writing f32 partials; a second pass sums them and applies the epilogue.
+static int choose_split_k(const GemmParams& p, const GemmEpilogue& ep, int64_t m_tiles, int sm_count)
+{
+	if (!env_on("GGML_B200_GEMM_SPLITK", true)) return 1;
+	if (ep.geglu || p.c_dt != DT_F16 || (p.N % 4) || (p.ldc % 4) || ((uintptr_t)p.C & 7)) return 1;
+	if (ep.residual && (ep.residual_dt != DT_F16)) return 1;
+	if (ep.bias && ((uintptr_t)ep.bias & 15)) return 1;
+	const int64_t tiles = m_tiles * ((p.N + 255) / 256);
+	if (tiles * 2 > sm_count || p.num_kb < 128) return 1;       // measured: K = 11520 -7 %, K = 23040 -18 %, but K = 5120 +25 % (the partial sums cost more than they save)
+	int S = (int)std::min<int64_t>(8, sm_count / tiles);
+	S = std::min(S, p.num_kb / 16);
+	return S >= 2 ? S : 1;
+}
+
+static void finish_setup_split_k(GemmTC* g, const GemmEpilogue& ep, int64_t m_tiles, int S)
+{
+	GemmParams& p = g->p;
+	SplitK& k = g->sk;
+	k.S = S; k.C = p.C; k.ldc = p.ldc;
+	k.bias = ep.bias; k.rowvec = ep.rowvec; k.rowvec_dt = ep.rowvec_dt; k.rowvec_stride = ep.rowvec_stride;
+	k.rows_per_image = ep.rows_per_image > 0 ? ep.rows_per_image : 1;
+	k.residual = ep.residual; k.ldr = ep.ldr; k.act = ep.act;
+	CUDA_CHECK(cudaMalloc(&k.ws, (size_t)S * p.M * p.N * sizeof(float)));
+	p.split_k = S; p.kbps = (p.num_kb + S - 1) / S;
+	p.BN = (int)std::min<int64_t>(256, (p.N + 15) / 16 * 16);
+	const size_t stage = (size_t)BM * BK * 2 + (size_t)p.BN * BK * 2;
+	p.stages = (int)std::max<size_t>(2, std::min<size_t>(MAX_STAGES, (196 * 1024) / stage));
+	g->smem = p.stages * stage + 1024 + (2 * MAX_STAGES + 1) * 8 + 32 + EPI_MAX_IMG * 256 * 4;
+	g->grid = dim3((unsigned)((p.N + p.BN - 1) / p.BN), (unsigned)m_tiles, (unsigned)S);
+	// the GEMM kernel writes raw f32 partial sums; everything else happens in the reduction pass
+	p.C = k.ws; p.c_dt = DT_F32; p.ldc = p.N;
+	p.bias = nullptr; p.rowvec = nullptr; p.residual = nullptr; p.act = U_NONE; p.rows_per_image = 1;
+	if (getenv("GGML_B200_GEMM_DEBUG"))
+		B200_LOG("gemm M=%d N=%d K=%d conv=%d m_tiles=%lld -> split-K %d x %d k-blocks, BN=%d, grid %u x %u x %u, stages %d", p.M, p.N, p.K, p.conv,
+			(long long)m_tiles, S, p.kbps, p.BN, g->grid.x, g->grid.y, g->grid.z, p.stages);
+}
 
 static bool persistent_eligible(const GemmParams& p, const GemmEpilogue& ep)
 {
@@ -914,7 +1001,9 @@ GemmTC* gemm_tc_prepare(const __half* A, int64_t lda, const __half* B, int64_t l
 	p.M = (int)M; p.N = (int)N; p.K = (int)K; p.num_kb = (int)((K + BK - 1) / BK);
 	p.C = C; p.c_dt = c_dt; p.ldc = ldc;
 	int64_t m_tiles = (M + BM - 1) / BM;
-	if (persistent_eligible(p, ep)) {
+	const int split = choose_split_k(p, ep, m_tiles, sm_count);
+	if (split > 1) finish_setup_split_k(g, ep, m_tiles, split);
+	else if (persistent_eligible(p, ep)) {
 		finish_setup_persistent(g, ep, m_tiles, sm_count);
 		cuuint64_t dc[2] = { (cuuint64_t)(ep.geglu ? N / 2 : N), (cuuint64_t)M }, sc[1] = { (cuuint64_t)ldc * 2 };
 		cuuint32_t bc[2] = { STG_CHUNK_COLS, BM };
@@ -962,7 +1051,9 @@ GemmTC* conv3x3_tc_prepare(const __half* x, int64_t n_img, int64_t H, int64_t W,
 	p.tiles_h = (int)((H + p.bh - 1) / p.bh);
 	int64_t tiles_i = (n_img + p.bi - 1) / p.bi;
 	int64_t m_tiles = (int64_t)p.tiles_w * p.tiles_h * tiles_i;
-	if (persistent_eligible(p, ep)) {
+	const int split = choose_split_k(p, ep, m_tiles, sm_count);
+	if (split > 1) finish_setup_split_k(g, ep, m_tiles, split);
+	else if (persistent_eligible(p, ep)) {
 		finish_setup_persistent(g, ep, m_tiles, sm_count);
 		cuuint64_t dc[4] = { (cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img };
 		cuuint64_t sc[3] = { (cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2 };
@@ -1036,6 +1127,14 @@ void gemm_tc_launch(cudaStream_t s, GemmTC* g)
 		CUDA_CHECK(cudaLaunchKernelEx(&cfg, persistent_variant(g->p), g->tmA, g->tmB, g->tmC, g->tmR, g->p));
 	} else gemm_tc_kernel<<<g->grid, 192, g->smem, s>>>(g->tmA, g->tmB, g->p);
 	g_stats.kernel_launches++;
+	if (g->sk.S > 1) {
+		const SplitK& k = g->sk;
+		const long long total = (long long)g->p.M * (g->p.N / 4);
+		const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 8);
+		splitk_reduce_kernel<<<blocks, 256, 0, s>>>(k.ws, k.S, g->p.M, g->p.N, (__half*)k.C, k.ldc, k.bias, k.rowvec, k.rowvec_dt, k.rowvec_stride,
+			k.rows_per_image, k.act, (const __half*)k.residual, k.ldr);
+		g_stats.kernel_launches++;
+	}
 }
 
 static int max_active_clusters(int csize, int sm_count)
@@ -1072,6 +1171,7 @@ void gemm_tc_free(GemmTC* g)
 		}
 		cudaFree(g->p.trace);
 	}
+	if (g->sk.ws) cudaFree(g->sk.ws);
 	delete g;
 }
 
