@@ -147,3 +147,59 @@ def test_reference_clip_on_oracle_matches_hf_clip_text_model(oracle_built, tmp_p
     err = np.abs(ref - want).max() / np.abs(want).max()
     print("reference CLIP on the oracle vs HF CLIPTextModel: max-rel err %.2e" % err)
     assert err <= 2e-3
+
+
+def test_reference_sdxl_second_encoder_and_pooled_feature_match_hf(oracle_built, tmp_path):
+    """SDXL's second text encoder (OpenCLIP bigG/14, 32 blocks): the penultimate hidden state without the final norm
+    (what goes into the 2048-wide context, mlimgsynth.c:1502-1563) and the pooled feature -- ln_final of the last block at
+    the first end-of-text token times text_projection (clip.c:418-437), the head of the label vector -- against
+    CLIPTextModelWithProjection."""
+    torch = pytest.importorskip("torch")
+    tr = pytest.importorskip("transformers")
+    from mlimgsynth_b200.api import MLIS_Tensor
+    import gen_weights
+    lib_path = os.path.join(oracle_built, "libmlimgsynth_cpu.so")
+    if not os.path.exists(lib_path):
+        pytest.skip("oracle/_ref/libmlimgsynth_cpu.so not built")
+    wpath = str(tmp_path / "clip_sdxl.safetensors")
+    gen_weights.write_safetensors(wpath, gen_weights.build_spec("sdxl", parts=("clip",)), 1234, "f16")
+    L = C.CDLL(lib_path, mode=C.RTLD_LOCAL)
+    L.mlis_ctx_create_i.restype = C.c_void_p; L.mlis_ctx_create_i.argtypes = [C.c_int]
+    L.mlis_ctx_destroy.argtypes = [C.POINTER(C.c_void_p)]
+    L.mlis_option_set_str.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+    L.mlis_errstr_get.restype = C.c_char_p; L.mlis_errstr_get.argtypes = [C.c_void_p]
+    L.mlis_clip_text_encode.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(MLIS_Tensor), C.POINTER(MLIS_Tensor), C.c_int, C.c_int]
+    L.mlis_text_tokenize.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.POINTER(C.c_int32)), C.c_int]
+    SUBMODEL_CLIP2, NO_NORM = 5, 1
+    h = C.c_void_p(L.mlis_ctx_create_i(0x000402))
+    for k, v in (("backend", "CPU"), ("model", wpath), ("model_type", "sdxl")):
+        assert L.mlis_option_set_str(h, k.encode(), v.encode()) >= 0, L.mlis_errstr_get(h)
+    e, f = MLIS_Tensor(), MLIS_Tensor()
+    assert L.mlis_clip_text_encode(h, PROMPT, C.byref(e), None, SUBMODEL_CLIP2, NO_NORM) >= 1, L.mlis_errstr_get(h)
+    assert L.mlis_clip_text_encode(h, PROMPT, None, C.byref(f), SUBMODEL_CLIP2, 0) >= 1, L.mlis_errstr_get(h)
+    assert [int(x) for x in e.n][:2] == [1280, 77] and int(f.n[0]) == 1280
+    emb = np.ctypeslib.as_array(e.d, shape=(77 * 1280,)).reshape(77, 1280).copy()
+    feat = np.ctypeslib.as_array(f.d, shape=(1280,)).copy()
+    pt = C.POINTER(C.c_int32)()
+    nt = L.mlis_text_tokenize(h, PROMPT, C.byref(pt), SUBMODEL_CLIP2)
+    toks = [int(pt[i]) for i in range(nt)]
+    L.mlis_ctx_destroy(C.byref(h))
+
+    sd = read_safetensors(wpath, "conditioner.embedders.1.model.")
+    hf = openclip_to_hf(sd, 1280)
+    hf["text_projection.weight"] = sd["text_projection"].t().contiguous()       # OpenCLIP applies x @ P, nn.Linear x @ W^T
+    cfg = tr.CLIPTextConfig(vocab_size=49408, hidden_size=1280, intermediate_size=5120, num_hidden_layers=32, num_attention_heads=20,
+                            max_position_embeddings=77, hidden_act="gelu_pytorch_tanh", projection_dim=1280,
+                            eos_token_id=49407, pad_token_id=0, bos_token_id=49406)
+    m = tr.CLIPTextModelWithProjection(cfg).eval()
+    missing, unexpected = m.load_state_dict(hf, strict=False)
+    assert not missing and not unexpected
+    ids = [49406] + toks + [49407]
+    ids += [0] * (77 - len(ids))
+    with torch.no_grad():
+        o = m(input_ids=torch.tensor([ids]), output_hidden_states=True)
+    want_emb, want_feat = o.hidden_states[-2][0].numpy(), o.text_embeds[0].numpy()
+    e1 = np.abs(emb - want_emb).max() / np.abs(want_emb).max()
+    e2 = np.abs(feat - want_feat).max() / np.abs(want_feat).max()
+    print("SDXL encoder 2 on the oracle vs HF: hidden %.2e, pooled feature %.2e" % (e1, e2))
+    assert e1 <= 3e-3 and e2 <= 3e-3
