@@ -268,15 +268,15 @@ def main():
         g_fl = prof.get("gemm_tc", {}).get("tflop", 0) + prof.get("conv3x3_tc", {}).get("tflop", 0)
         g_n = prof.get("gemm_tc", {}).get("launches", 0) + prof.get("conv3x3_tc", {}).get("launches", 0)
         achieved = g_fl / (g_ms / 1e3) if g_ms else 0.0
-        traffic = None      # DRAM bytes per launch of the same kernel family from the committed ncu capture (profiles/)
+        traffic, traffic_launches = None, 0      # DRAM bytes per launch of the same kernel family from the committed ncu capture (profiles/)
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")))
-            traffic = tj["dram_bytes_per_launch"]
+            traffic = tj["dram_bytes_per_launch"]; traffic_launches = tj["launches"]
         except Exception:
             pass
         roof = {"bound": "tensor", "kernel": "gemm_tc_persistent_kernel (tcgen05 cta_group::2 GEMM + implicit 3x3 conv; all linear / conv launches of one UNet evaluation)", "achieved": achieved, "peak": pk["bf16_tflops"],
                 "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"], "traffic": traffic,
-                "traffic_note": "dram__bytes_read+write per launch, ncu capture of all %d launches of one evaluation (profiles/r1_ncu_gemm_traffic.md); algorithmic bytes per launch %.1f MB" % (g_n, (prof.get("gemm_tc", {}).get("gb", 0) + prof.get("conv3x3_tc", {}).get("gb", 0)) * 1e3 / max(g_n, 1)),
+                "traffic_note": "dram__bytes_read+write per launch, ncu capture of all %d tcgen05 GEMM/conv launches of one evaluation (profiles/r1_ncu_gemm_traffic.md); algorithmic bytes per launch %.1f MB" % (traffic_launches, (prof.get("gemm_tc", {}).get("gb", 0) + prof.get("conv3x3_tc", {}).get("gb", 0)) * 1e3 / max(g_n, 1)),
                 "algorithmic_tflop_per_launch": g_fl / 1e12 / max(g_n, 1), "peak_source": pk["src"],
                 "launches_per_unet_eval": g_n, "avg_launch_us": g_ms * 1e3 / g_n if g_n else None,
                 "unet_eval_ms_batch%d" % (2 * B): nfe_ms,
