@@ -277,7 +277,7 @@ def main():
         roof = {"bound": "tensor", "kernel": "gemm_tc_persistent_kernel (tcgen05 cta_group::2 GEMM + implicit 3x3 conv; all linear / conv launches of one UNet evaluation)", "achieved": achieved, "peak": pk["bf16_tflops"],
                 "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"], "traffic": traffic,
                 "traffic_note": "dram__bytes_read+write per launch, ncu capture of all %d tcgen05 GEMM/conv launches of one evaluation (profiles/r1_ncu_gemm_traffic.md); algorithmic bytes per launch %.1f MB" % (traffic_launches, (prof.get("gemm_tc", {}).get("gb", 0) + prof.get("conv3x3_tc", {}).get("gb", 0)) * 1e3 / max(g_n, 1)),
-                "algorithmic_tflop_per_launch": g_fl / 1e12 / max(g_n, 1), "peak_source": pk["src"],
+                "algorithmic_tflop_per_launch": g_fl / max(g_n, 1), "peak_source": pk["src"],
                 "launches_per_unet_eval": g_n, "avg_launch_us": g_ms * 1e3 / g_n if g_n else None,
                 "unet_eval_ms_batch%d" % (2 * B): nfe_ms,
                 "unet_tflops": FLOP_PER_NFE_SD15_512 * 2 * B / (nfe_ms / 1e3) / 1e12,
