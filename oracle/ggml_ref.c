@@ -16,7 +16,13 @@
  * call sites (cited per function). The reference's host logic (tokenizer,
  * prompt parser, Philox RNG, sampler, solvers) is NOT restated here: the
  * oracle uses the reference's own compiled objects for those, and those ARE
- * pinned by the reference's known-answer tests (tests/test_oracle_host.py).
+ * pinned by the reference's known-answer tests (tests/test_host_cpu.py).
+ * What stands in for the missing ggml vectors is a set of independent anchors on the
+ * canonical PyTorch definitions of the same operators and models (all CPU tests):
+ * tests/test_oracle_vs_torch.py (ops and blocks), tests/test_clip_vs_hf.py (the
+ * reference's clip.c on this oracle vs Hugging Face CLIP), tests/test_unet_vs_torch.py
+ * (one full denoising step vs an LDM UNet in torch, SD1.x and SD2.x),
+ * tests/test_vae_vs_torch.py (VAE decode / encode): agreement 3e-4 .. 1e-3.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load anything built from this file.
