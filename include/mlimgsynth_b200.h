@@ -114,11 +114,16 @@ MLIS_Tensor* mlis_tensor_get(MLIS_Ctx* ctx, MLIS_TensorId id);
 const MLIS_BackendInfo* mlis_backend_info_get(MLIS_Ctx* ctx, unsigned idx, int flags);
 
 const char* mlis_stage_str(MLIS_Stage id);
+const char* mlis_stage_desc(MLIS_Stage id);
+MLIS_Stage mlis_stage_fromz(const char* str);
+const char* mlis_loglvl_str(MLIS_LogLvl id);
+MLIS_LogLvl mlis_loglvl_fromz(const char* str);
 const char* mlis_method_str(MLIS_Method id);
 MLIS_Method mlis_method_fromz(const char* str);
 const char* mlis_sched_str(MLIS_Scheduler id);
 MLIS_Scheduler mlis_sched_fromz(const char* str);
 const char* mlis_model_type_str(MLIS_ModelType id);
+const char* mlis_model_type_desc(MLIS_ModelType id);
 MLIS_ModelType mlis_model_type_fromz(const char* str);
 const char* mlis_option_str(MLIS_Option id);
 MLIS_Option mlis_option_fromz(const char* str);

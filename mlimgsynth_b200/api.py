@@ -27,34 +27,40 @@ CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(MLIS_Progress)
 _lib = None
 
 
+def bind(L, extensions=True):
+    """Declare the mlis_* prototypes (include/mlimgsynth_b200.h) on a loaded library. `extensions=False` binds only the
+    functions of the reference's own header (any library with that ABI can then be driven by `Ctx(_lib=...)`)."""
+    L.mlis_ctx_create_i.restype = C.c_void_p
+    L.mlis_ctx_create_i.argtypes = [C.c_int]
+    L.mlis_ctx_destroy.argtypes = [C.POINTER(C.c_void_p)]
+    L.mlis_errstr_get.restype = C.c_char_p
+    L.mlis_errstr_get.argtypes = [C.c_void_p]
+    L.mlis_option_set_str.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+    L.mlis_generate.argtypes = [C.c_void_p]
+    L.mlis_setup.argtypes = [C.c_void_p]
+    L.mlis_image_get.restype = C.POINTER(MLIS_Image)
+    L.mlis_image_get.argtypes = [C.c_void_p, C.c_int]
+    L.mlis_infotext_get.restype = C.c_char_p
+    L.mlis_infotext_get.argtypes = [C.c_void_p, C.c_int]
+    L.mlis_tensor_get.restype = C.POINTER(MLIS_Tensor)
+    L.mlis_tensor_get.argtypes = [C.c_void_p, C.c_int]
+    L.mlis_text_tokenize.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.POINTER(C.c_int32)), C.c_int]
+    L.mlis_clip_text_encode.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(MLIS_Tensor), C.POINTER(MLIS_Tensor), C.c_int, C.c_int]
+    L.mlis_image_decode.argtypes = [C.c_void_p, C.POINTER(MLIS_Tensor), C.POINTER(MLIS_Tensor), C.c_int]
+    L.mlis_image_encode.argtypes = [C.c_void_p, C.POINTER(MLIS_Tensor), C.POINTER(MLIS_Tensor), C.c_int]
+    L.mlis_tensor_resize.argtypes = [C.POINTER(MLIS_Tensor), C.c_int, C.c_int, C.c_int, C.c_int]
+    L.mlis_tensor_free.argtypes = [C.POINTER(MLIS_Tensor)]
+    if extensions:
+        L.mlis_unet_eval.argtypes = [C.c_void_p, C.POINTER(MLIS_Tensor), C.POINTER(MLIS_Tensor), C.POINTER(MLIS_Tensor), C.c_float, C.POINTER(MLIS_Tensor)]
+    return L
+
+
 def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(HOST_LIB) or not os.path.exists(ENGINE_LIB):
             raise EngineMissing("%s / %s not built (run __graft_entry__.build()); there is no CPU fallback" % (HOST_LIB, ENGINE_LIB))
-        L = C.CDLL(HOST_LIB, mode=C.RTLD_LOCAL)
-        L.mlis_ctx_create_i.restype = C.c_void_p
-        L.mlis_ctx_create_i.argtypes = [C.c_int]
-        L.mlis_ctx_destroy.argtypes = [C.POINTER(C.c_void_p)]
-        L.mlis_errstr_get.restype = C.c_char_p
-        L.mlis_errstr_get.argtypes = [C.c_void_p]
-        L.mlis_option_set_str.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
-        L.mlis_generate.argtypes = [C.c_void_p]
-        L.mlis_setup.argtypes = [C.c_void_p]
-        L.mlis_image_get.restype = C.POINTER(MLIS_Image)
-        L.mlis_image_get.argtypes = [C.c_void_p, C.c_int]
-        L.mlis_infotext_get.restype = C.c_char_p
-        L.mlis_infotext_get.argtypes = [C.c_void_p, C.c_int]
-        L.mlis_tensor_get.restype = C.POINTER(MLIS_Tensor)
-        L.mlis_tensor_get.argtypes = [C.c_void_p, C.c_int]
-        L.mlis_text_tokenize.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.POINTER(C.c_int32)), C.c_int]
-        L.mlis_clip_text_encode.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(MLIS_Tensor), C.POINTER(MLIS_Tensor), C.c_int, C.c_int]
-        L.mlis_image_decode.argtypes = [C.c_void_p, C.POINTER(MLIS_Tensor), C.POINTER(MLIS_Tensor), C.c_int]
-        L.mlis_image_encode.argtypes = [C.c_void_p, C.POINTER(MLIS_Tensor), C.POINTER(MLIS_Tensor), C.c_int]
-        L.mlis_unet_eval.argtypes = [C.c_void_p, C.POINTER(MLIS_Tensor), C.POINTER(MLIS_Tensor), C.POINTER(MLIS_Tensor), C.c_float, C.POINTER(MLIS_Tensor)]
-        L.mlis_tensor_resize.argtypes = [C.POINTER(MLIS_Tensor), C.c_int, C.c_int, C.c_int, C.c_int]
-        L.mlis_tensor_free.argtypes = [C.POINTER(MLIS_Tensor)]
-        _lib = L
+        _lib = bind(C.CDLL(HOST_LIB, mode=C.RTLD_LOCAL))
     return _lib
 
 
@@ -78,8 +84,8 @@ def _from_tensor(t):
 
 
 class Ctx:
-    def __init__(self, **opts):
-        self.L = lib()
+    def __init__(self, _lib=None, **opts):
+        self.L = _lib if _lib is not None else lib()
         self.h = C.c_void_p(self.L.mlis_ctx_create_i(0x000402))
         self._cb = None
         for k, v in opts.items():

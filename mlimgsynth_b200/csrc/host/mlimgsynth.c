@@ -73,11 +73,14 @@ static const char* k_options[] = { "none", "backend", "model", "tae", "lora_dir"
 	"s_ancestral", "image", "image_mask", "no_decode", "tensor_use_flags", "seed", "vae_tile", "unet_split", "threads",
 	"dump_flags", "aux_dir", "callback", "error_handler", "log_level", "model_type", "weight_type", "no_prompt_parse" };
 
-/* identifier comparison: '-' == '_', '+' == 'p' (for "dpm++2m"), otherwise exact */
+/* identifier comparison as the reference header documents it (mlimgsynth.h:435-441: "CFG_SCALE" = "cfg_scale" =
+ * "cfg-scale"): case-insensitive, '-' == '_', '+' == 'p' (for "dpm++2m"). The reference's strsl_cmpz_id
+ * (mlimgsynth.c:157-170) intends the same; its upper-case branch subtracts 'A' without adding 'a' back, so there only
+ * lower-case names match -- every name the reference accepts is accepted here with the same meaning. */
 static bool id_eq(const char* s, const char* name)
 {
 	for (; *s && *name; ++s, ++name) {
-		char c = *s == '-' ? '_' : *s == '+' ? 'p' : *s;
+		char c = *s == '-' ? '_' : *s == '+' ? 'p' : (*s >= 'A' && *s <= 'Z') ? (char)(*s - 'A' + 'a') : *s;
 		if (c != *name) return false;
 	}
 	return !*s && !*name;
@@ -88,7 +91,25 @@ static int enum_from(const char* s, const char* const* names, int n, int dflt)
 	return dflt;
 }
 #define NAMES(a) a, (int)(sizeof(a) / sizeof(a[0]))
+static const char* k_stage_desc[] = { "Idle", "Conditioning encoding", "Image encoding", "Image decoding", "Denoising" };
+static const char* k_model_desc[] = { "None", "Stable Diffusion 1.x", "Stable Diffusion 2.x", "Stable Diffusion XL" };
+static const struct { const char* name; int id; } k_loglvls[] = {
+	{ "none", MLIS_LOGLVL_NONE }, { "error", MLIS_LOGLVL_ERROR }, { "warning", MLIS_LOGLVL_WARNING }, { "info", MLIS_LOGLVL_INFO },
+	{ "verbose", MLIS_LOGLVL_VERBOSE }, { "debug", MLIS_LOGLVL_DEBUG }, { "max", MLIS_LOGLVL_MAX } };
 const char* mlis_stage_str(MLIS_Stage id) { return (unsigned)id < 5 ? k_stages[id] : "???"; }
+const char* mlis_stage_desc(MLIS_Stage id) { return (unsigned)id < 5 ? k_stage_desc[id] : "???"; }
+MLIS_Stage mlis_stage_fromz(const char* s) { return (MLIS_Stage)enum_from(s, NAMES(k_stages), -1); }
+const char* mlis_model_type_desc(MLIS_ModelType id) { return (unsigned)id < 4 ? k_model_desc[id] : "???"; }
+const char* mlis_loglvl_str(MLIS_LogLvl id)
+{
+	for (unsigned i = 0; i < sizeof(k_loglvls) / sizeof(k_loglvls[0]); ++i) if ((int)id == k_loglvls[i].id) return k_loglvls[i].name;
+	return "???";
+}
+MLIS_LogLvl mlis_loglvl_fromz(const char* s)
+{
+	for (unsigned i = 0; i < sizeof(k_loglvls) / sizeof(k_loglvls[0]); ++i) if (id_eq(s, k_loglvls[i].name)) return (MLIS_LogLvl)k_loglvls[i].id;
+	return (MLIS_LogLvl)-1;
+}
 const char* mlis_method_str(MLIS_Method id) { return (unsigned)id < 6 ? k_methods[id] : "???"; }
 MLIS_Method mlis_method_fromz(const char* s) { return (MLIS_Method)enum_from(s, NAMES(k_methods), -1); }
 const char* mlis_sched_str(MLIS_Scheduler id) { return (unsigned)id < 3 ? k_scheds[id] : "???"; }
@@ -96,7 +117,7 @@ MLIS_Scheduler mlis_sched_fromz(const char* s) { return (MLIS_Scheduler)enum_fro
 const char* mlis_model_type_str(MLIS_ModelType id) { return (unsigned)id < 4 ? k_models[id] : "???"; }
 MLIS_ModelType mlis_model_type_fromz(const char* s) { return (MLIS_ModelType)enum_from(s, NAMES(k_models), -1); }
 const char* mlis_option_str(MLIS_Option id) { return (unsigned)id <= MLIS_OPT__LAST ? k_options[id] : "???"; }
-MLIS_Option mlis_option_fromz(const char* s) { return (MLIS_Option)enum_from(s, NAMES(k_options), 0); }
+MLIS_Option mlis_option_fromz(const char* s) { return (MLIS_Option)enum_from(s, NAMES(k_options), -1); }   /* -1 when unknown, as mlimgsynth.c:301 */
 
 /* ------------------------------------------------------------------ errors, callbacks */
 static int fail(MLIS_Ctx* S, int code, const char* where)
@@ -290,7 +311,9 @@ static int option_apply(MLIS_Ctx* S, MLIS_Option id, const Arg* a, int n_arg)
 	case MLIS_OPT_ERROR_HANDLER: S->errh = (MLIS_ErrorHandler)a[0].p; S->errh_user = a[1].p2; break;
 	case MLIS_OPT_LOG_LEVEL: {
 		int l = (int)a[0].i;
-		if ((l & 0xf00) == 0x100) g_log_level += l & 0xff; else if ((l & 0xf00) == 0x200) g_log_level -= l & 0xff; else g_log_level = l;
+		/* increase starts directly from INFO (options_set.c.h:229-238) */
+		if ((l & 0xf00) == 0x100) { if (g_log_level < LOG_INFO) g_log_level = LOG_INFO; else g_log_level += l & 0xff; }
+		else if ((l & 0xf00) == 0x200) g_log_level -= l & 0xff; else g_log_level = l;
 	} break;
 	default: FAIL(MLIS_E_UNK_OPT, "unknown option %d", (int)id);
 	}
@@ -317,7 +340,7 @@ static const char* option_sig(MLIS_Option id)
 
 int mlis_option_set(MLIS_Ctx* S, MLIS_Option id, ...)
 {
-	if (id <= 0 || id > MLIS_OPT__LAST) { mlis_err_set("unknown option %d", (int)id); return fail(S, MLIS_E_UNK_OPT, "mlis_option_set"); }
+	if ((int)id <= 0 || (int)id > MLIS_OPT__LAST) { mlis_err_set("unknown option %d", (int)id); return fail(S, MLIS_E_UNK_OPT, "mlis_option_set"); }
 	const char* sig = option_sig(id);
 	Arg a[4]; memset(a, 0, sizeof(a));
 	va_list ap; va_start(ap, id);
@@ -341,12 +364,13 @@ done:
 int mlis_option_set_str(MLIS_Ctx* S, const char* name, const char* value)
 {
 	MLIS_Option id = mlis_option_fromz(name);
-	if (id <= 0) { mlis_err_set("unknown option '%s'", name); return fail(S, MLIS_E_UNK_OPT, "mlis_option_set_str"); }
+	if ((int)id <= 0) { mlis_err_set("unknown option '%s'", name); return fail(S, MLIS_E_UNK_OPT, "mlis_option_set_str"); }
 	const char* sig = option_sig(id);
 	Arg a[4]; memset(a, 0, sizeof(a));
 	char buf[4][1024];
 	int n = 0;
 	const char* v = value ? value : "";
+	if (id == MLIS_OPT_SEED && !*v) return 1;      /* empty string: keep the (random) seed, options_set.c.h:163-164 */
 	bool whole = (id == MLIS_OPT_MODEL || id == MLIS_OPT_TAE || id == MLIS_OPT_AUX_DIR || id == MLIS_OPT_LORA_DIR ||
 		id == MLIS_OPT_PROMPT || id == MLIS_OPT_NPROMPT);
 	for (; sig[n]; ++n) {
@@ -370,7 +394,8 @@ int mlis_option_set_str(MLIS_Ctx* S, const char* name, const char* value)
 			if (id == MLIS_OPT_METHOD) x = mlis_method_fromz(a[n].s);
 			else if (id == MLIS_OPT_SCHEDULER) x = mlis_sched_fromz(a[n].s);
 			else if (id == MLIS_OPT_MODEL_TYPE) x = mlis_model_type_fromz(a[n].s);
-			else if (id == MLIS_OPT_WEIGHT_TYPE) x = !strcmp(a[n].s, "f16") ? GGML_TYPE_F16 : !strcmp(a[n].s, "f32") ? GGML_TYPE_F32 : -1;
+			else if (id == MLIS_OPT_WEIGHT_TYPE) x = id_eq(a[n].s, "f16") ? GGML_TYPE_F16 : id_eq(a[n].s, "f32") ? GGML_TYPE_F32 : -1;
+			else if (id == MLIS_OPT_LOG_LEVEL) x = mlis_loglvl_fromz(a[n].s);      /* level names (options_set.c.h:220-226) */
 			if (x < 0) { x = (int)strtol(a[n].s, &tail, 0); if (tail == a[n].s) goto bad; }
 			a[n].i = x;
 		} break;
