@@ -56,6 +56,7 @@ GGML_API void ggml_b200_box_downsample(float* out, const float* in, int w, int h
 /* LoRA merge on device (lora.c:46-78): W[n1][n0] (f16) <- f16( f32(W) + scale * (up[n1][r] . down[r][n0]) ),
  * operands f16, products accumulated in f32, ONE f16 rounding per merge (same as the reference). */
 GGML_API void ggml_b200_lora_merge_f16(void* w_dev, const void* down_dev, const void* up_dev, int64_t n0, int64_t n1, int r, float scale);
+GGML_API void ggml_b200_lora_merge_f32(void* w_dev, const void* down_dev, const void* up_dev, int64_t n0, int64_t n1, int r, float scale);
 
 /* Non-finite guard (unet.c:487): accumulates into a device flag; _check downloads and clears it. */
 GGML_API void ggml_b200_nonfinite_accumulate(const float* x, int64_t n);

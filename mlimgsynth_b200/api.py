@@ -158,12 +158,15 @@ class Ctx:
         n = self._chk(self.L.mlis_text_tokenize(self.h, text.encode(), C.byref(pt), model))
         return [int(pt[i]) for i in range(n)]
 
-    def clip_encode(self, text, model=SUBMODEL_CLIP, feat=False, flags=0):
+    def clip_encode(self, text, model=SUBMODEL_CLIP, feat=False, flags=0, both=False):
+        """embed [77,d] (feat=False), pooled projected feature [d] (feat=True), or (embed, feat) from one call (both=True)."""
         e, f = MLIS_Tensor(), MLIS_Tensor()
-        self._chk(self.L.mlis_clip_text_encode(self.h, text.encode(), None if feat else C.byref(e), C.byref(f) if feat else None, model, flags))
-        out = _from_tensor(f if feat else e)
-        self.L.mlis_tensor_free(C.byref(f if feat else e))
-        return out
+        want_e, want_f = both or not feat, both or feat
+        self._chk(self.L.mlis_clip_text_encode(self.h, text.encode(), C.byref(e) if want_e else None, C.byref(f) if want_f else None, model, flags))
+        oe = _from_tensor(e) if want_e else None
+        of = _from_tensor(f) if want_f else None
+        self.L.mlis_tensor_free(C.byref(e)); self.L.mlis_tensor_free(C.byref(f))
+        return (oe, of) if both else (of if feat else oe)
 
     def unet_eval(self, x, cond, label, sigma):
         tx, tc = _to_tensor(x), _to_tensor(cond)

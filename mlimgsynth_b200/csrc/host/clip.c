@@ -288,8 +288,9 @@ int clip_text_encode(ClipState* S, MLCtx* C, const ClipParams* P, const char* tp
 		S->t_embed = mlb_clip_text(C, S->t_tok, P, clip_skip, norm);
 		MLTensor* result = S->t_embed;
 		S->t_feat = NULL;
+		/* both results come from the same graph when features are requested, as in the reference (clip.c:439-488) */
+		ggml_set_output(S->t_embed);
 		if (feat) result = S->t_feat = mlb_clip_text_proj(C, S->t_embed, -1);
-		else ggml_set_output(S->t_embed);
 		mlctx_tensor_add(C, "text", result);
 		C->c.tprefix = tprefix;
 		CHECK(mlctx_prep(C));
@@ -297,7 +298,7 @@ int clip_text_encode(ClipState* S, MLCtx* C, const ClipParams* P, const char* tp
 	}
 	ggml_backend_tensor_set(S->t_tok, tokens, 0, sizeof(int32_t) * P->n_token);
 	CHECK(mlctx_compute(C));
-	if (embed && !feat) {
+	if (embed) {
 		ht_resize(embed, P->d_embed, P->n_token, 1, 1);
 		ggml_backend_tensor_get(S->t_embed, embed->d, 0, ht_count(embed) * sizeof(float));
 	}

@@ -26,7 +26,44 @@ static float scalar_of(const TSEntry* e)
 	return v;
 }
 
-int lora_apply(TStore* dst, TStore* lora, float mult)
+/* One tensor: W <- W + scale * up . down in the weight type `ts_dt` (TS_F16 / TS_F32), on the device. */
+static int lora_apply_one(TStore* dst, TSEntry* w, const TSEntry* ld, const TSEntry* lu, float scale, int ts_dt)
+{
+	int64_t r = ld->shape[ld->ndim - 1], n0 = tsentry_count(ld) / r, n1 = tsentry_count(lu) / r;
+	const size_t es = ts_dt == TS_F32 ? 4 : 2;
+	void *t0 = NULL, *t1 = NULL, *t2 = NULL; char* dev = NULL; uint8_t* merged = NULL;
+	int R = 1;
+	const void* hw = tsentry_as(w, ts_dt, &t0);
+	const void* hd = tsentry_as(ld, ts_dt, &t1);
+	const void* hu = tsentry_as(lu, ts_dt, &t2);
+	if (!hw || !hd || !hu) { mlis_err_set("lora: unsupported dtype for %s", w->key); R = -1; goto end; }
+	size_t bw = (size_t)n0 * n1 * es, bd = (size_t)n0 * r * es, bu = (size_t)n1 * r * es;
+	/* the index guarantees nbytes == count x element size (tstore.c), so these reads stay inside the mappings */
+	dev = ggml_b200_malloc(bw + bd + bu + 64);
+	if (!dev) { mlis_err_set("lora: device allocation failed"); R = -1; goto end; }
+	char* ddown = dev + (bw + 15) / 16 * 16; char* dup = ddown + (bd + 15) / 16 * 16;
+	ggml_b200_upload(dev, hw, bw); ggml_b200_upload(ddown, hd, bd); ggml_b200_upload(dup, hu, bu);
+	if (ts_dt == TS_F32) ggml_b200_lora_merge_f32(dev, ddown, dup, n0, n1, (int)r, scale);
+	else ggml_b200_lora_merge_f16(dev, ddown, dup, n0, n1, (int)r, scale);
+	merged = xmalloc(bw);
+	ggml_b200_download(merged, dev, bw);
+	/* NaN/Inf guard on the first element, like lora.c:80-87 */
+	float first;
+	if (ts_dt == TS_F32) memcpy(&first, merged, 4); else { _Float16 h; memcpy(&h, merged, 2); first = (float)h; }
+	if (!(first - first == 0)) { mlis_err_set("NaN in LoRA result"); R = -1; goto end; }
+	int64_t shape[4] = { w->shape[0], w->shape[1], w->shape[2], w->shape[3] };
+	int nd = w->ndim;
+	char* wkey = xstrdup(w->key);
+	tstore_add(dst, wkey, ts_dt, nd, shape, merged, bw, true);      /* the store owns `merged` now */
+	merged = NULL;
+	free(wkey);
+end:
+	if (dev) ggml_b200_free(dev);
+	free(merged); free(t0); free(t1); free(t2);
+	return R;
+}
+
+int lora_apply(TStore* dst, TStore* lora, float mult, int ts_dt)
 {
 	static const char suffix[] = ".lora_down.weight";
 	char key[320];
@@ -48,37 +85,17 @@ int lora_apply(TStore* dst, TStore* lora, float mult)
 		TSEntry* la = tstore_find(lora, key);
 
 		/* shapes in ggml order: down [n0.., r], up [r.., n1] with r the outer dim of down (lora.c:15-26) */
-		int64_t r = ld->shape[ld->ndim - 1], n0 = tsentry_count(ld) / r, n1 = tsentry_count(lu) / r;
-		if (w->ndim < 2 || ld->ndim != w->ndim || lu->ndim != w->ndim || tsentry_count(w) != n0 * n1)
+		int64_t r = ld->ndim ? ld->shape[ld->ndim - 1] : 0;
+		if (r <= 0) FAIL(-1, "lora down tensor has no rank dimension: %s", ld->key);
+		int64_t n0 = tsentry_count(ld) / r, n1 = tsentry_count(lu) / r;
+		if (w->ndim < 2 || ld->ndim != w->ndim || lu->ndim != w->ndim || tsentry_count(w) != n0 * n1 || tsentry_count(lu) != n1 * r)
 			FAIL(-1, "lora up/down invalid shapes for %s", w->key);
 		float scale = 1;
 		if (ls) scale = scalar_of(ls);
 		else if (la) scale = scalar_of(la) / r;
 		scale *= mult;
 		if (!(scale > 0)) FAIL(-1, "lora scale must be positive (%g)", scale);
-
-		void *t0, *t1, *t2;
-		const void* hw = tsentry_as(w, TS_F16, &t0);
-		const void* hd = tsentry_as(ld, TS_F16, &t1);
-		const void* hu = tsentry_as(lu, TS_F16, &t2);
-		if (!hw || !hd || !hu) FAIL(-1, "lora: unsupported dtype for %s", w->key);
-		size_t bw = (size_t)n0 * n1 * 2, bd = (size_t)n0 * r * 2, bu = (size_t)n1 * r * 2;
-		char* dev = ggml_b200_malloc(bw + bd + bu + 64);
-		char* ddown = dev + (bw + 15) / 16 * 16; char* dup = ddown + (bd + 15) / 16 * 16;
-		ggml_b200_upload(dev, hw, bw); ggml_b200_upload(ddown, hd, bd); ggml_b200_upload(dup, hu, bu);
-		ggml_b200_lora_merge_f16(dev, ddown, dup, n0, n1, (int)r, scale);
-		uint8_t* merged = xmalloc(bw);
-		ggml_b200_download(merged, dev, bw);
-		ggml_b200_free(dev);
-		free(t0); free(t1); free(t2);
-		/* NaN/Inf guard on the first element, like lora.c:80-87 */
-		_Float16 first; memcpy(&first, merged, 2);
-		if (!((float)first - (float)first == 0)) { free(merged); FAIL(-1, "NaN in LoRA result"); }
-		int64_t shape[4] = { w->shape[0], w->shape[1], w->shape[2], w->shape[3] };
-		int nd = w->ndim;
-		char* wkey = xstrdup(w->key);
-		tstore_add(dst, wkey, TS_F16, nd, shape, merged, bw, true);
-		free(wkey);
+		CHECK(lora_apply_one(dst, w, ld, lu, scale, ts_dt));
 		n_applied++;
 	}
 	return n_applied;

@@ -103,6 +103,9 @@ static int upload_param(MLCtx* C, MLCtxEntry* e)
 		FAIL(-1, "tensor '%s': wrong element count %lld (graph wants %lld)", e->key, (long long)tsentry_count(s), (long long)ggml_nelements(t));
 	int want = t->type == GGML_TYPE_F16 ? TS_F16 : t->type == GGML_TYPE_F32 ? TS_F32 : -1;
 	if (want < 0) FAIL(-1, "tensor '%s': unsupported graph type %s", e->key, ggml_type_name(t->type));
+	const size_t src_es = s->dtype == TS_F32 ? 4 : 2;
+	if (s->nbytes < (size_t)tsentry_count(s) * src_es)      /* never read past the entry's bytes in the mapping */
+		FAIL(-1, "tensor '%s': %zu bytes stored, %zu needed", e->key, s->nbytes, (size_t)tsentry_count(s) * src_es);
 	void* tmp = NULL;
 	const void* src = tsentry_as(s, want, &tmp);
 	if (!src) FAIL(-1, "tensor '%s': unsupported file dtype", e->key);

@@ -221,6 +221,8 @@ static int model_type_set(MLIS_Ctx* S, int mt)
 static int lora_add(MLIS_Ctx* S, const char* name, size_t len, float mult, int from_prompt)
 {
 	if (!(mult >= 0 && mult <= 1)) FAIL(MLIS_E_OPT_VALUE, "lora multiplier out of range [0,1]");
+	/* the option accepts 0 (options_set.c.h:38) but the merge requires scale > 0 (lora.c:42): a zero-weight LoRA is a no-op */
+	if (mult == 0) { log_warn("LoRA '%.*s' has multiplier 0: ignored", (int)len, name); return 1; }
 	char path[1024];
 	bool is_path = memchr(name, '/', len) != NULL || (len > 12 && !memcmp(name + len - 12, ".safetensors", 12));
 	if (is_path || !S->lora_dir) snprintf(path, sizeof(path), "%.*s", (int)len, name);
@@ -479,8 +481,9 @@ static int setup(MLIS_Ctx* S)
 		double t0 = time_now();
 		for (int i = 0; i < S->n_loras; ++i) {
 			TStore tl; memset(&tl, 0, sizeof(tl));
-			CHECK(tstore_read_safetensors(&tl, S->loras[i].path, lora_name_conv, NULL));
-			int r = lora_apply(&S->tstore, &tl, S->loras[i].mult);
+			int rr = tstore_read_safetensors(&tl, S->loras[i].path, lora_name_conv, NULL);
+			if (rr < 0) { tstore_free(&tl); return rr; }
+			int r = lora_apply(&S->tstore, &tl, S->loras[i].mult, S->wtype == GGML_TYPE_F32 ? TS_F32 : TS_F16);
 			tstore_free(&tl);
 			if (r < 0) return r;
 			log_info("LoRA '%s' x%g: %d tensors merged", S->loras[i].path, S->loras[i].mult, r);

@@ -56,7 +56,8 @@ void tstore_free(TStore* S)
 {
 	for (int i = 0; i < S->n; ++i) { free(S->e[i].key); if (S->e[i].owned) free((void*)S->e[i].data); }
 	free(S->e); free(S->hash);
-	if (S->map) munmap(S->map, S->map_size);
+	for (int i = 0; i < S->n_map; ++i) munmap(S->maps[i].p, S->maps[i].size);
+	free(S->maps);
 	memset(S, 0, sizeof(*S));
 }
 
@@ -107,19 +108,14 @@ static bool js_skip(JS* j)   /* skip any value */
 	return true;
 }
 
-int tstore_read_safetensors(TStore* S, const char* path, ts_name_conv conv, const char* prefix)
+static size_t dtype_size(int dtype) { return dtype == TS_F32 ? 4 : (dtype == TS_F16 || dtype == TS_BF16) ? 2 : 0; }
+
+/* Parses the header of a mapped file into `S`. Nothing from the file is trusted: every entry must lie inside the data
+ * section and its byte range must be exactly shape x element size, so consumers may read tsentry_count() elements. */
+static int safetensors_index(TStore* S, const uint8_t* base, uint64_t file_size, uint64_t hlen, ts_name_conv conv, const char* prefix)
 {
-	int fd = open(path, O_RDONLY);
-	if (fd < 0) FAIL(-6, "could not open '%s'", path);
-	struct stat st; fstat(fd, &st);
-	void* map = mmap(NULL, st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
-	close(fd);
-	if (map == MAP_FAILED) FAIL(-1, "could not map '%s'", path);
-	const uint8_t* base = map;
-	uint64_t hlen; memcpy(&hlen, base, 8);
-	if (st.st_size < 8 || hlen + 8 > (uint64_t)st.st_size) { munmap(map, st.st_size); FAIL(-1, "'%s' is not a safetensors file", path); }
-	S->map = map; S->map_size = st.st_size;
 	const uint8_t* data0 = base + 8 + hlen;
+	const uint64_t data_size = file_size - 8 - hlen;
 	JS j = { (const char*)base + 8, (const char*)base + 8 + hlen };
 	if (!js_ch(&j, '{')) FAIL(-1, "safetensors header: expected object");
 	char key[256], conv_key[256], full[320], field[32], dt[16];
@@ -128,7 +124,7 @@ int tstore_read_safetensors(TStore* S, const char* path, ts_name_conv conv, cons
 		if (!js_str(&j, key, sizeof(key)) || !js_ch(&j, ':')) FAIL(-1, "safetensors header: bad key");
 		if (!strcmp(key, "__metadata__")) { if (!js_skip(&j)) FAIL(-1, "safetensors header: bad metadata"); continue; }
 		if (!js_ch(&j, '{')) FAIL(-1, "safetensors header: bad entry '%s'", key);
-		int64_t shape[8], off0 = 0, off1 = 0; int nd = 0; dt[0] = 0;
+		int64_t shape[8], off0 = -1, off1 = -1; int nd = 0; dt[0] = 0;
 		while (!js_ch(&j, '}')) {
 			js_ch(&j, ',');
 			if (!js_str(&j, field, sizeof(field)) || !js_ch(&j, ':')) FAIL(-1, "safetensors header: bad field in '%s'", key);
@@ -147,10 +143,16 @@ int tstore_read_safetensors(TStore* S, const char* path, ts_name_conv conv, cons
 		else snprintf(conv_key, sizeof(conv_key), "%s", key);
 		snprintf(full, sizeof(full), "%s%s", prefix ? prefix : "", conv_key);
 		int dtype = !strcmp(dt, "F32") ? TS_F32 : !strcmp(dt, "F16") ? TS_F16 : !strcmp(dt, "BF16") ? TS_BF16 : TS_OTHER;
-		if (nd > 4) continue;
-		int64_t rs[4] = {1, 1, 1, 1};
-		for (int i = 0; i < nd; ++i) rs[i] = shape[nd - 1 - i];
-		if ((uint64_t)off1 > (uint64_t)st.st_size - 8 - hlen || off1 < off0) FAIL(-1, "tensor '%s' data out of file bounds", key);
+		if (nd > 4 || dtype == TS_OTHER) continue;      /* not consumable by the engine (no quantised / integer weights on this path) */
+		int64_t rs[4] = {1, 1, 1, 1}, count = 1;
+		for (int i = 0; i < nd; ++i) {
+			rs[i] = shape[nd - 1 - i];
+			if (rs[i] < 0 || (rs[i] && count > INT64_MAX / 8 / rs[i])) FAIL(-1, "tensor '%s': invalid shape", key);
+			count *= rs[i];
+		}
+		if (off0 < 0 || off1 < off0 || (uint64_t)off1 > data_size) FAIL(-1, "tensor '%s' data out of file bounds", key);
+		if ((uint64_t)(off1 - off0) != (uint64_t)count * dtype_size(dtype))
+			FAIL(-1, "tensor '%s': %lld bytes in the file, shape x dtype needs %lld", key, (long long)(off1 - off0), (long long)(count * (int64_t)dtype_size(dtype)));
 		if (r == 2) {
 			/* fused OpenCLIP attn.in_proj_{weight,bias}: split the outer dim in q,k,v thirds (mlimgsynth.c:990-1030) */
 			const char* tail = strstr(full, "in_proj_");
@@ -170,6 +172,26 @@ int tstore_read_safetensors(TStore* S, const char* path, ts_name_conv conv, cons
 		tstore_add(S, full, dtype, nd, rs, data0 + off0, (size_t)(off1 - off0), false);
 	}
 	return S->n;
+}
+
+int tstore_read_safetensors(TStore* S, const char* path, ts_name_conv conv, const char* prefix)
+{
+	int fd = open(path, O_RDONLY);
+	if (fd < 0) FAIL(-6, "could not open '%s'", path);
+	struct stat st;
+	if (fstat(fd, &st) < 0 || st.st_size < 8) { close(fd); FAIL(-1, "'%s' is not a safetensors file", path); }
+	void* map = mmap(NULL, st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+	close(fd);
+	if (map == MAP_FAILED) FAIL(-1, "could not map '%s'", path);
+	uint64_t hlen; memcpy(&hlen, map, 8);
+	if (hlen > (uint64_t)st.st_size - 8) { munmap(map, st.st_size); FAIL(-1, "'%s' is not a safetensors file", path); }
+	int n_before = S->n;
+	int r = safetensors_index(S, map, (uint64_t)st.st_size, hlen, conv, prefix);
+	if (r < 0 && S->n == n_before) { munmap(map, st.st_size); return r; }    /* nothing references the mapping */
+	/* a store may hold several files (model + TAE): every mapping lives until tstore_free */
+	struct TSMap m = { map, (size_t)st.st_size };
+	ARR_PUSH(S->maps, S->n_map, S->cap_map, m);
+	return r;
 }
 
 /* ---- dtype conversion on the host (tensorstore.c:185-230 role) ---- */

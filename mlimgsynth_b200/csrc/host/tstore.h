@@ -19,7 +19,7 @@ typedef struct TSEntry {
 typedef struct TStore {
 	TSEntry* e; int n, cap;
 	int*     hash; int hash_cap;       /* open addressing over key strings */
-	void*    map; size_t map_size;     /* mmap of the file */
+	struct TSMap { void* p; size_t size; } *maps; int n_map, cap_map;   /* one mapping per file read into the store */
 } TStore;
 
 /* Reads the index of a safetensors file. Every key is passed through `conv` (NULL: identity);

@@ -108,15 +108,21 @@ __global__ void box_downsample_kernel(float* out, const float* in, int w, int h,
 	out[i] = s / (fw * fh);
 }
 
-__global__ void lora_merge_kernel(__half* W, const __half* down, const __half* up, long long n0, long long n1, int r, float scale)
+__device__ __forceinline__ float lora_ld(const __half* p) { return __half2float(*p); }
+__device__ __forceinline__ float lora_ld(const float* p) { return *p; }
+__device__ __forceinline__ void lora_st(__half* p, float v) { *p = __float2half_rn(v); }
+__device__ __forceinline__ void lora_st(float* p, float v) { *p = v; }
+// W += scale * up . down in the weight type T (lora.c:46-78: operands in wtype, product and sum in f32, ONE rounding back to wtype)
+template <typename T>
+__global__ void lora_merge_kernel(T* W, const T* down, const T* up, long long n0, long long n1, int r, float scale)
 {
 	long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;   // input-feature index (contiguous)
 	long long j = blockIdx.y;                                         // output-feature index
 	if (i >= n0) return;
 	float acc = 0.f;
-	for (int k = 0; k < r; ++k) acc += __half2float(up[j * r + k]) * __half2float(down[(long long)k * n0 + i]);
-	float w = __half2float(W[j * n0 + i]);
-	W[j * n0 + i] = __float2half_rn(__fadd_rn(w, __fmul_rn(acc, scale)));
+	for (int k = 0; k < r; ++k) acc += lora_ld(up + j * r + k) * lora_ld(down + (long long)k * n0 + i);
+	float w = lora_ld(W + j * n0 + i);
+	lora_st(W + j * n0 + i, __fadd_rn(w, __fmul_rn(acc, scale)));
 }
 
 __global__ void nonfinite_kernel(const float* x, long long n, int* flag)
@@ -219,7 +225,14 @@ void ggml_b200_lora_merge_f16(void* w_dev, const void* down_dev, const void* up_
 {
 	if (DRY) return;
 	dim3 grid(nblk(n0, 256), (unsigned)n1);
-	lora_merge_kernel<<<grid, 256, 0, b200_engine_stream()>>>((__half*)w_dev, (const __half*)down_dev, (const __half*)up_dev, n0, n1, r, scale);
+	lora_merge_kernel<__half><<<grid, 256, 0, b200_engine_stream()>>>((__half*)w_dev, (const __half*)down_dev, (const __half*)up_dev, n0, n1, r, scale);
+	g_stats.kernel_launches++;
+}
+void ggml_b200_lora_merge_f32(void* w_dev, const void* down_dev, const void* up_dev, int64_t n0, int64_t n1, int r, float scale)
+{
+	if (DRY) return;
+	dim3 grid(nblk(n0, 256), (unsigned)n1);
+	lora_merge_kernel<float><<<grid, 256, 0, b200_engine_stream()>>>((float*)w_dev, (const float*)down_dev, (const float*)up_dev, n0, n1, r, scale);
 	g_stats.kernel_launches++;
 }
 void ggml_b200_nonfinite_accumulate(const float* x, int64_t n)

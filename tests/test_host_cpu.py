@@ -205,7 +205,7 @@ def test_tensor_store_reads_and_converts_safetensors(tmp_path):
 
     class TStore(C.Structure):
         _fields_ = [("e", C.POINTER(TSEntry)), ("n", C.c_int), ("cap", C.c_int), ("hash", C.POINTER(C.c_int)), ("hash_cap", C.c_int),
-                    ("map", C.c_void_p), ("map_size", C.c_size_t)]
+                    ("maps", C.c_void_p), ("n_map", C.c_int), ("cap_map", C.c_int)]
     L = C.CDLL(mlimgsynth_b200.HOST_LIB)
     L.tstore_read_safetensors.argtypes = [C.POINTER(TStore), C.c_char_p, C.c_void_p, C.c_char_p]
     L.tstore_find.restype = C.POINTER(TSEntry); L.tstore_find.argtypes = [C.POINTER(TStore), C.c_char_p]
@@ -242,4 +242,31 @@ def test_tensor_store_reads_and_converts_safetensors(tmp_path):
     assert k_v
     v16, ev = fetch(k_v[0], 1, np.float16, 24)
     assert list(ev.shape)[:3] == [4, 2, 3] and np.array_equal(v16.view(np.uint16), a16.reshape(-1).view(np.uint16))
+    # a second file read into the same store (model + TAE) keeps BOTH mappings alive until tstore_free
+    assert L.tstore_read_safetensors(C.byref(S), path.encode(), None, b"second.") >= 1 and S.n_map == 2
+    w2, _ = fetch(k_w[0], 0, np.float32, 35)
+    assert np.array_equal(w2, a32.reshape(-1))
     L.tstore_free(C.byref(S))
+    assert S.n == 0 and S.n_map == 0
+
+    # the header is not trusted: entries whose byte range is negative, outside the file or not shape x dtype are rejected
+    def write(name, header_obj, payload, hlen=None):
+        hj = json.dumps(header_obj, separators=(",", ":")).encode()
+        q = str(tmp_path / name)
+        with open(q, "wb") as f:
+            f.write(struct.pack("<Q", len(hj) if hlen is None else hlen)); f.write(hj); f.write(payload)
+        return q
+    key = "model.diffusion_model.time_embed.0.weight"
+    bad = [
+        write("neg.safetensors", {key: {"dtype": "F32", "shape": [2, 2], "data_offsets": [-16, 0]}}, b"\0" * 16),
+        write("short.safetensors", {key: {"dtype": "F32", "shape": [4, 4], "data_offsets": [0, 16]}}, b"\0" * 16),      # 16 bytes for 64
+        write("past.safetensors", {key: {"dtype": "F16", "shape": [8], "data_offsets": [8, 24]}}, b"\0" * 16),          # beyond the data section
+        write("rev.safetensors", {key: {"dtype": "F16", "shape": [8], "data_offsets": [16, 0]}}, b"\0" * 16),
+        write("hdr.safetensors", {key: {"dtype": "F16", "shape": [8], "data_offsets": [0, 16]}}, b"\0" * 16, hlen=1 << 40),
+    ]
+    tiny = str(tmp_path / "tiny.safetensors"); open(tiny, "wb").write(b"abc")
+    for q in bad + [tiny]:
+        S2 = TStore()
+        assert L.tstore_read_safetensors(C.byref(S2), q.encode(), conv, None) < 0, q
+        assert S2.n == 0 and S2.n_map == 0, q                         # nothing indexed, mapping released
+        L.tstore_free(C.byref(S2))
