@@ -148,6 +148,17 @@ float  mlis_tensor_similarity(const MLIS_Tensor*, const MLIS_Tensor*);
  * Used by the parity tests and the benchmark's per-NFE timing. */
 int mlis_unet_eval(MLIS_Ctx* ctx, const MLIS_Tensor* x, const MLIS_Tensor* cond, const MLIS_Tensor* label, float sigma, MLIS_Tensor* dx);
 
+/* VAE decode tiles spread across GPUs (one process per GPU). The reference decodes the tiles of `vae_tile` serially
+ * (vae.c:331-391); they are independent, so rank r of `world` decodes tiles r, r + world, ... of the reference's row-major
+ * tile list into consecutive slots of a CALLER-owned device buffer (f32, tile_w_px * tile_h_px * 3 floats per slot,
+ * ceil(n_tiles / world) slots). The caller gathers the buffers of all ranks on one rank (NCCL, device to device; layout
+ * [world][slots_per_worker][slot]) and calls merge there: tiles are pasted in the reference's order (later tiles
+ * overwrite earlier ones, vae.c:365-387), then (x+1)/2, RGB8 pack and the usual mlis_image_get()/MLIS_TENSOR_IMAGE.
+ * With world = 1 this is the serial tiled decode. */
+int mlis_b200_vae_tile_plan(MLIS_Ctx* ctx, int lw, int lh, int* n_tiles, int* tile_w_px, int* tile_h_px);
+int mlis_b200_vae_tiles_decode(MLIS_Ctx* ctx, const MLIS_Tensor* latent, int rank, int world, float* tiles_dev);
+int mlis_b200_vae_tiles_merge(MLIS_Ctx* ctx, int lw, int lh, const float* gathered_dev, int world, int slots_per_worker, MLIS_Tensor* image);
+
 #ifdef __cplusplus
 }
 #endif

@@ -185,6 +185,27 @@ class Ctx:
         self.L.mlis_tensor_free(C.byref(img))
         return out
 
+    # ---- VAE decode tiles spread across GPUs (include/mlimgsynth_b200.h)
+    def vae_tile_plan(self, lw, lh):
+        """(n_tiles, tile_w_px, tile_h_px) of the current `vae_tile` option for a latent of lw x lh."""
+        n, tw, th = C.c_int(), C.c_int(), C.c_int()
+        self._chk(self.L.mlis_b200_vae_tile_plan(self.h, lw, lh, C.byref(n), C.byref(tw), C.byref(th)))
+        return n.value, tw.value, th.value
+
+    def vae_tiles_decode(self, latent, rank, world, tiles_dev_ptr):
+        """Decode tiles rank, rank + world, ... of `latent` [1,4,lh,lw] into the caller's device buffer."""
+        tl = _to_tensor(latent)
+        self._chk(self.L.mlis_b200_vae_tiles_decode(self.h, C.byref(tl), rank, world, C.c_void_p(tiles_dev_ptr)))
+
+    def vae_tiles_merge(self, lw, lh, gathered_dev_ptr, world, slots_per_worker, want_float=False):
+        """Paste the gathered tiles in the reference's order; the image is then available through image(0)."""
+        img = MLIS_Tensor() if want_float else None
+        self._chk(self.L.mlis_b200_vae_tiles_merge(self.h, lw, lh, C.c_void_p(gathered_dev_ptr), world, slots_per_worker, C.byref(img) if want_float else None))
+        if want_float:
+            out = _from_tensor(img)
+            self.L.mlis_tensor_free(C.byref(img))
+            return out
+
     def encode(self, image):
         ti = _to_tensor(image)
         lat = MLIS_Tensor()

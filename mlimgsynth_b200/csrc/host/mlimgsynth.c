@@ -634,6 +634,8 @@ static void image_sync_host(MLIS_Ctx* S)
 	S->image_host_stale = false;
 }
 
+static int image_finish(MLIS_Ctx* S, int w, int h, int n);
+
 /* latent_dev [lw,lh,4,n] -> image_dev [8lw,8lh,3,n] (+ RGB8 pack), all on the device */
 static int decode_dev(MLIS_Ctx* S, int lw, int lh, int n)
 {
@@ -658,6 +660,13 @@ static int decode_dev(MLIS_Ctx* S, int lw, int lh, int n)
 		if (S->flags & CF_USE_TAE) CHECK(sdtae_decode(&S->st_tdec, graph_ctx_init(S, &S->ctx_tdec), S->tae_p, l, lw, lh, im));
 		else CHECK(sdvae_decode(&S->st_vdec, graph_ctx_init(S, &S->ctx_vdec), S->vae_p, l, lw, lh, im, S->vae_tile));
 	}
+	return image_finish(S, w, h, n);
+}
+
+/* image_dev [w,h,3,n] in [0,1] -> NaN check, RGB8 pack on the device, ONE synchronising download */
+static int image_finish(MLIS_Ctx* S, int w, int h, int n)
+{
+	size_t per = (size_t)w * h * 3;
 	ggml_b200_nonfinite_accumulate(S->image_dev, (int64_t)(per * n));
 	/* float -> RGB8: clamp(v*255, 0, 255) truncated (mlimgsynth.c:112-129) */
 	if (per * n > S->u8_dev_n) { ggml_b200_free(S->u8_dev); S->u8_dev = ggml_b200_malloc(per * n); S->u8_dev_n = per * n; }
@@ -711,6 +720,44 @@ int mlis_image_decode(MLIS_Ctx* S, const MLIS_Tensor* latent, MLIS_Tensor* image
 	image_sync_host(S);
 	if ((HTensor*)image != &S->image) ht_copy((HTensor*)image, &S->image);
 	image->flags |= HT_READY;
+	return 1;
+}
+
+/* ---- VAE decode tiles spread across GPUs (BASELINE configs[4]); see include/mlimgsynth_b200.h ---- */
+int mlis_b200_vae_tile_plan(MLIS_Ctx* S, int lw, int lh, int* n_tiles, int* tile_w_px, int* tile_h_px)
+{
+	API_TRY(setup(S), "mlis_b200_vae_tile_plan");
+	VaeTilePlan T;
+	int nt = sdvae_tile_plan(S->vae_p, lw, lh, S->vae_tile, &T);
+	if (n_tiles) *n_tiles = nt;
+	if (tile_w_px) *tile_w_px = T.n0 * T.f;
+	if (tile_h_px) *tile_h_px = T.n1 * T.f;
+	return nt;
+}
+
+int mlis_b200_vae_tiles_decode(MLIS_Ctx* S, const MLIS_Tensor* latent, int rank, int world, float* tiles_dev)
+{
+	API_TRY(setup(S), "mlis_b200_vae_tiles_decode");
+	if (latent->n[2] != 4 || latent->n[3] != 1) { mlis_err_set("latent wrong shape"); return fail(S, -1, "mlis_b200_vae_tiles_decode"); }
+	if (world < 1 || rank < 0 || rank >= world) { mlis_err_set("invalid rank %d of %d", rank, world); return fail(S, -1, "mlis_b200_vae_tiles_decode"); }
+	int lw = latent->n[0], lh = latent->n[1];
+	size_t cnt = (size_t)lw * lh * 4;
+	dev_reserve(&S->latent_dev, &S->latent_dev_n, cnt);
+	ggml_b200_upload(S->latent_dev, latent->d, cnt * sizeof(float));
+	API_TRY(sdvae_decode_tiles(&S->st_vdec, graph_ctx_init(S, &S->ctx_vdec), S->vae_p, S->latent_dev, lw, lh, S->vae_tile, rank, world, tiles_dev),
+		"mlis_b200_vae_tiles_decode");
+	ggml_b200_synchronize();       /* the caller hands tiles_dev to its collective on another stream */
+	return 1;
+}
+
+int mlis_b200_vae_tiles_merge(MLIS_Ctx* S, int lw, int lh, const float* gathered_dev, int world, int slots_per_worker, MLIS_Tensor* image)
+{
+	API_TRY(setup(S), "mlis_b200_vae_tiles_merge");
+	int f = S->vae_p->f_down, w = lw * f, h = lh * f;
+	dev_reserve(&S->image_dev, &S->image_dev_n, (size_t)w * h * 3);
+	API_TRY(sdvae_merge_tiles(S->vae_p, lw, lh, S->vae_tile, gathered_dev, world, slots_per_worker, S->image_dev), "mlis_b200_vae_tiles_merge");
+	API_TRY(image_finish(S, w, h, 1), "mlis_b200_vae_tiles_merge");
+	if (image) { image_sync_host(S); if ((HTensor*)image != &S->image) ht_copy((HTensor*)image, &S->image); image->flags |= HT_READY; }
 	return 1;
 }
 

@@ -214,6 +214,61 @@ int sdvae_decode(CodecState* S, MLCtx* C, const VaeParams* P, const float* laten
 	return 1;
 }
 
+/* ---- tiled decode split across workers (VAE tiles are independent given the fixed tile graph, vae.c:343-346) ----
+ * A worker (GPU rank) decodes the tiles  first, first + stride, ...  of the reference's row-major tile list into consecutive
+ * slots of `tiles_dev`; after the slots of all workers are gathered, the merge pastes them in the reference's visiting order
+ * so that overlaps resolve exactly as in the serial loop (later tiles overwrite earlier ones, vae.c:365-387). */
+int sdvae_tile_plan(const VaeParams* P, int lw, int lh, int tile_px, VaeTilePlan* T)
+{
+	const int f = P->f_down, k = 8;
+	T->k = k; T->f = f;
+	T->n0 = tile_extent(tile_px, f, k, lw); T->n1 = tile_extent(tile_px, f, k, lh);
+	const bool single = (T->n0 == lw && T->n1 == lh);
+	T->step0 = single ? T->n0 : T->n0 - 2 * k; T->step1 = single ? T->n1 : T->n1 - 2 * k;
+	T->nt0 = (lw + T->step0 - 1) / T->step0; T->nt1 = (lh + T->step1 - 1) / T->step1;
+	T->tile_elems = (size_t)T->n0 * f * T->n1 * f * P->ch_x;
+	return T->nt0 * T->nt1;
+}
+
+int sdvae_decode_tiles(CodecState* S, MLCtx* C, const VaeParams* P, const float* latent_dev, int lw, int lh, int tile_px,
+	int first, int stride, float* tiles_dev)
+{
+	VaeTilePlan T;
+	const int nt = sdvae_tile_plan(P, lw, lh, tile_px, &T);
+	if (first < 0 || stride < 1) FAIL(-1, "invalid tile assignment %d/%d", first, stride);
+	CHECK(codec_prepare(S, C, CODEC_VAE_DEC, T.n0, T.n1, 1, P));
+	float* tin = (float*)S->t_in->data;
+	for (int t = first, slot = 0; t < nt; t += stride, ++slot) {
+		int t1 = t / T.nt0, t0 = t % T.nt0;
+		int i1 = t1 * T.step1; if (i1 > lh - T.n1) i1 = lh - T.n1;
+		int i0 = t0 * T.step0; if (i0 > lw - T.n0) i0 = lw - T.n0;
+		copy_region(tin, T.n0, T.n1, 0, 0, latent_dev, lw, lh, i0, i1, T.n0, T.n1, 4);
+		CHECK(mlctx_compute(C));
+		ggml_b200_copy(tiles_dev + T.tile_elems * slot, S->t_out->data, T.tile_elems * sizeof(float));
+	}
+	return nt;
+}
+
+int sdvae_merge_tiles(const VaeParams* P, int lw, int lh, int tile_px, const float* gathered_dev, int world, int slots_per_worker, float* image_dev)
+{
+	VaeTilePlan T;
+	const int nt = sdvae_tile_plan(P, lw, lh, tile_px, &T);
+	const int f = T.f, k = T.k, ow = lw * f, oh = lh * f, tw_o = T.n0 * f, th_o = T.n1 * f;
+	if (world < 1 || slots_per_worker * world < nt) FAIL(-1, "tile buffer too small: %d x %d slots for %d tiles", world, slots_per_worker, nt);
+	for (int t = 0; t < nt; ++t) {            /* the reference's order: t1 outer, t0 inner */
+		int t1 = t / T.nt0, t0 = t % T.nt0;
+		int i1 = t1 * T.step1; if (i1 > lh - T.n1) i1 = lh - T.n1;
+		int i0 = t0 * T.step0; if (i0 > lw - T.n0) i0 = lw - T.n0;
+		const float* tout = gathered_dev + T.tile_elems * ((size_t)(t % world) * slots_per_worker + t / world);
+		if (nt == 1) { copy_region(image_dev, ow, oh, 0, 0, tout, tw_o, th_o, 0, 0, tw_o, th_o, P->ch_x); break; }
+		int d0 = i0 ? k : 0, d1 = i1 ? k : 0;
+		int c0 = T.n0 == lw ? T.n0 : T.n0 - k, c1 = T.n1 == lh ? T.n1 : T.n1 - k;      /* same kept region as run_tiled */
+		copy_region(image_dev, ow, oh, (i0 + d0) * f, (i1 + d1) * f, tout, tw_o, th_o, d0 * f, d1 * f, c0 * f, c1 * f, P->ch_x);
+	}
+	ggml_b200_affine(image_dev, image_dev, 1, 0.5f, 0, (int64_t)ow * oh * P->ch_x);   /* (x+1)/2 (vae.h:43-47) */
+	return nt;
+}
+
 /* Untiled decode of nb latents in ONE graph run: the images of a batch are independent, so the decoder is
  * built with a batch dimension -- the 64x64 / 128x128 levels get GEMM rows from all images and every launch is shared.
  * Returns 0 (nothing done) when the requested tile size makes the decode tiled: the caller then decodes image by image

@@ -23,6 +23,14 @@ enum { CODEC_VAE_DEC = 1, CODEC_VAE_ENC = 2, CODEC_TAE_DEC = 3, CODEC_TAE_ENC = 
 int sdvae_decode(CodecState* S, MLCtx* C, const VaeParams* P, const float* latent_dev, int lw, int lh, float* image_dev, int tile_px);
 /* nb latents [lw,lh,4,nb] -> images [8lw,8lh,3,nb] in one run of a batched decoder graph; returns 0 if tile_px asks for tiling */
 int sdvae_decode_batch(CodecState* S, MLCtx* C, const VaeParams* P, const float* latent_dev, int lw, int lh, int nb, float* image_dev, int tile_px);
+/* Tiled decode split across workers: plan (tile list geometry of vae.c:331-368), decode of the tiles first, first+stride, ...
+ * into consecutive slots of tiles_dev (raw decoder output, tile_elems floats each), and the merge of the gathered slots
+ * (tile t lives at slot (t % world) * slots_per_worker + t / world) in the reference's row-major order + (x+1)/2. */
+typedef struct VaeTilePlan { int n0, n1, nt0, nt1, step0, step1, k, f; size_t tile_elems; } VaeTilePlan;
+int sdvae_tile_plan(const VaeParams* P, int lw, int lh, int tile_px, VaeTilePlan* plan);
+int sdvae_decode_tiles(CodecState* S, MLCtx* C, const VaeParams* P, const float* latent_dev, int lw, int lh, int tile_px,
+	int first, int stride, float* tiles_dev);
+int sdvae_merge_tiles(const VaeParams* P, int lw, int lh, int tile_px, const float* gathered_dev, int world, int slots_per_worker, float* image_dev);
 /* image_dev [w,h,3] in [0,1] -> moments_dev [w/8,h/8,8] (mean | logvar), tiled like vae.c:222-316 */
 int sdvae_encode(CodecState* S, MLCtx* C, const VaeParams* P, const float* image_dev, int w, int h, float* moments_dev, int tile_px);
 int sdtae_decode(CodecState* S, MLCtx* C, const SdTaeParams* P, const float* latent_dev, int lw, int lh, float* image_dev);

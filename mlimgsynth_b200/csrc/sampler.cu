@@ -156,11 +156,16 @@ void ggml_b200_download(void* host, const void* dev, size_t bytes)
 	if (e != cudaSuccess) B200_FATAL("device work failed: %s", cudaGetErrorString(e));
 	g_stats.d2h_bytes += bytes;
 }
+// Dry-run mode (no GPU: "device" pointers are host allocations) still moves bytes for the pure data-movement helpers, so the
+// host-side tile split / merge logic can be exercised by the CPU tests; nothing that computes runs there.
 void ggml_b200_copy(void* dst, const void* src, size_t bytes)
-{ if (DRY) return; CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, b200_engine_stream())); }
-void ggml_b200_memset(void* dev, int value, size_t bytes) { if (DRY) return; CUDA_CHECK(cudaMemsetAsync(dev, value, bytes, b200_engine_stream())); }
+{ if (DRY) { memmove(dst, src, bytes); return; } CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, b200_engine_stream())); }
+void ggml_b200_memset(void* dev, int value, size_t bytes) { if (DRY) { memset(dev, value, bytes); return; } CUDA_CHECK(cudaMemsetAsync(dev, value, bytes, b200_engine_stream())); }
 void ggml_b200_copy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes, size_t rows)
-{ if (DRY) return; CUDA_CHECK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, rows, cudaMemcpyDeviceToDevice, b200_engine_stream())); }
+{
+	if (DRY) { for (size_t r = 0; r < rows; ++r) memmove((char*)dst + r * dpitch, (const char*)src + r * spitch, width_bytes); return; }
+	CUDA_CHECK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, rows, cudaMemcpyDeviceToDevice, b200_engine_stream()));
+}
 void ggml_b200_affine(float* out, const float* in, float pre_add, float mul, float post_add, int64_t n)
 {
 	if (DRY) return;

@@ -61,6 +61,35 @@ def merge_tiles(canvas, decoded, w, h, tw, th, k, up):
     return canvas
 
 
+def vae_decode_tiled(ctx, latent, rank=None, world=None, dst=0):
+    """Tiled VAE decode with the tiles spread round-robin across the ranks of the default process group (BASELINE
+    configs[4]; reference loop vae.c:331-391). Each rank decodes its tiles on its own GPU into a device buffer, ONE NCCL
+    gather moves the tiles device-to-device to rank `dst`, which pastes them in the reference's row-major order
+    (mlis_b200_vae_tiles_merge). Returns the RGB8 image [H,W,3] on rank `dst`, None elsewhere. `latent`: [1,4,lh,lw].
+    Without an initialised process group (or world 1) this is the serial tiled decode through the same code."""
+    import torch
+    import torch.distributed as dist
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    lh, lw = latent.shape[-2:]
+    n_tiles, tw, th = ctx.vae_tile_plan(lw, lh)
+    slots = (n_tiles + world - 1) // world
+    mine = torch.empty((slots, 3 * th * tw), dtype=torch.float32, device="cuda")
+    torch.cuda.current_stream().synchronize()
+    ctx.vae_tiles_decode(latent, rank, world, mine.data_ptr())         # synchronises the engine stream before returning
+    if world > 1:
+        gathered = torch.empty((world, slots, 3 * th * tw), dtype=torch.float32, device="cuda") if rank == dst else None
+        dist.gather(mine, list(gathered.unbind(0)) if rank == dst else None, dst=dst)
+        torch.cuda.current_stream().synchronize()
+    else:
+        gathered = mine
+    if rank != dst:
+        return None
+    ctx.vae_tiles_merge(lw, lh, gathered.data_ptr(), world, slots)
+    return ctx.image(0)
+
+
 def gather_arrays(arr, dst=0, device=None):
     """Gather equally-shaped numpy arrays from all ranks to rank `dst` (returns the list there, None elsewhere).
     Works on any initialised torch.distributed backend; with NCCL pass the rank's CUDA device."""
