@@ -159,6 +159,9 @@ int mlis_b200_vae_tile_plan(MLIS_Ctx* ctx, int lw, int lh, int* n_tiles, int* ti
 int mlis_b200_vae_tiles_decode(MLIS_Ctx* ctx, const MLIS_Tensor* latent, int rank, int world, float* tiles_dev);
 int mlis_b200_vae_tiles_merge(MLIS_Ctx* ctx, int lw, int lh, const float* gathered_dev, int world, int slots_per_worker, MLIS_Tensor* image);
 
+/* Device pointer of the RGB8 images ([n][h][w][3] bytes) of the last generation / decode, for device-to-device gathers. */
+int mlis_b200_images_device(MLIS_Ctx* ctx, const uint8_t** dev, int* w, int* h, int* n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -185,6 +185,13 @@ class Ctx:
         self.L.mlis_tensor_free(C.byref(img))
         return out
 
+    def images_device(self):
+        """(device pointer, n, h, w) of the RGB8 images of the last generation as they lie in HBM."""
+        p, w, h, n = C.c_void_p(), C.c_int(), C.c_int(), C.c_int()
+        if self.L.mlis_b200_images_device(self.h, C.byref(p), C.byref(w), C.byref(h), C.byref(n)) < 0:
+            raise MLISError(self.L.mlis_errstr_get(self.h).decode())
+        return p.value, n.value, h.value, w.value
+
     # ---- VAE decode tiles spread across GPUs (include/mlimgsynth_b200.h)
     def vae_tile_plan(self, lw, lh):
         """(n_tiles, tile_w_px, tile_h_px) of the current `vae_tile` option for a latent of lw x lh."""

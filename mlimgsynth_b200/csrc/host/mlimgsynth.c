@@ -972,6 +972,18 @@ MLIS_Image* mlis_image_get(MLIS_Ctx* S, int idx)
 	return &S->imgex;
 }
 
+/* The RGB8 images of the last generation / decode as the pack kernel left them in HBM ([n][h][w][3] bytes): multi-GPU callers
+ * gather them device-to-device instead of re-uploading the host copies. Valid until the next generate / decode call. */
+int mlis_b200_images_device(MLIS_Ctx* S, const uint8_t** dev, int* w, int* h, int* n)
+{
+	if (!(S->image.flags & HT_READY) || !S->u8_dev) { snprintf(S->errstr, sizeof(S->errstr), "image not ready"); return -1; }
+	if (dev) *dev = S->u8_dev;
+	if (w) *w = S->img_w;
+	if (h) *h = S->img_h;
+	if (n) *n = S->img_n;
+	return 1;
+}
+
 const char* mlis_infotext_get(MLIS_Ctx* S, int idx) { (void)idx; return S->infotext; }
 
 MLIS_Tensor* mlis_tensor_get(MLIS_Ctx* S, MLIS_TensorId id)

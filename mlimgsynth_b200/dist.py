@@ -90,6 +90,40 @@ def vae_decode_tiled(ctx, latent, rank=None, world=None, dst=0):
     return ctx.image(0)
 
 
+class _DeviceBytes:
+    """Zero-copy view of foreign device memory for torch (CUDA array interface)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+_pinned = {}
+
+
+def gather_images_device(ctx, dst=0):
+    """Gather the RGB8 images of the last generation of every rank on rank `dst`: NCCL gather of the device buffers the
+    pack kernel wrote (no re-upload of host copies), then ONE device-to-host copy into pinned memory on `dst`.
+    Returns [world * n, h, w, 3] uint8 (numpy) there, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    ptr, n, h, w = ctx.images_device()
+    nbytes = n * h * w * 3
+    mine = torch.as_tensor(_DeviceBytes(ptr, nbytes), device="cuda")
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if rank == dst:
+        g = torch.empty((world, nbytes), dtype=torch.uint8, device="cuda")
+        dist.gather(mine, list(g.unbind(0)), dst=dst)
+        key = (world, nbytes)
+        if key not in _pinned:
+            _pinned.clear(); _pinned[key] = torch.empty((world, nbytes), dtype=torch.uint8, pin_memory=True)
+        host = _pinned[key]
+        host.copy_(g, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host.numpy().reshape(world * n, h, w, 3)
+    dist.gather(mine, None, dst=dst)
+    return None
+
+
 def gather_arrays(arr, dst=0, device=None):
     """Gather equally-shaped numpy arrays from all ranks to rank `dst` (returns the list there, None elsewhere).
     Works on any initialised torch.distributed backend; with NCCL pass the rank's CUDA device."""
