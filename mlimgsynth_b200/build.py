@@ -65,7 +65,7 @@ def build_host(engine_so, verbose=False, force=False):
         return out
     cmd = ["gcc", "-std=gnu11", "-O2", "-g", "-fPIC", "-shared", "-Wall", "-Wno-unused-function", "-fvisibility=default",
            "-I", os.path.join(ROOT, "include"), "-I", hdir, "-o", out] + srcs + \
-          ["-L", LIB, "-lggml_b200", "-Wl,-rpath,$ORIGIN", "-Wl,--no-undefined", "-lm", "-ldl"]
+          ["-L", LIB, "-lggml_b200", "-Wl,-rpath,$ORIGIN", "-Wl,-soname,libmlimgsynth_b200.so", "-Wl,--no-undefined", "-lm", "-ldl"]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)

@@ -435,6 +435,66 @@ void k_gemm_simt(cudaStream_t s, const View& c, const View& a, const View& b, bo
 	g_stats.kernel_launches++;
 }
 
+
+// ---- deterministic statistics (no floating-point atomics): every reduction below runs in an order fixed by indices,
+// never by arrival, so a GroupNorm -- and with it a whole graph run -- is bit-reproducible from run to run.
+// Block: per-thread channel sums -> shared memory -> per-channel sums over the block's pixel lanes (double) -> per-group
+// sums over the channels of the slab (double) -> partials[n][block][group]. The LAST block of an image to finish (ticket
+// counter) adds the partials of all blocks in block order and writes stats[n][group] = (sum, sum of squares).
+struct GnRed {
+	double* stats; double* partials; unsigned* counters;
+};
+__device__ __forceinline__ void gn_block_finish(const float* su, const float* sq, bool active, int ch_local, int plane, int planes, int slab, int slab_chunks,
+	int chunks, int cpg, int groups, int n, const GnRed& R, float* smf)
+{
+	// smf: [planes][slab_chunks * 8][2] floats, then (8-byte aligned) chs[slab_chunks * 8][2] doubles, then parts[4][groups * 2]
+	// doubles: gn_stats_smem() bytes
+	const int nch = slab_chunks * 8;
+	double* chs = reinterpret_cast<double*>(smf + (size_t)planes * nch * 2);
+	__shared__ unsigned s_last;
+	if (plane < planes) {
+		#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			float* d = smf + ((size_t)plane * nch + ch_local * 8 + j) * 2;
+			d[0] = active ? su[j] : 0.f; d[1] = active ? sq[j] : 0.f;
+		}
+	}
+	__syncthreads();
+	for (int c = threadIdx.x; c < nch; c += blockDim.x) {
+		double a = 0.0, b = 0.0;
+		for (int pl = 0; pl < planes; ++pl) { const float* d = smf + ((size_t)pl * nch + c) * 2; a += (double)d[0]; b += (double)d[1]; }
+		chs[c * 2] = a; chs[c * 2 + 1] = b;
+	}
+	__syncthreads();
+	const int c_lo = slab * nch, c_hi = min(chunks * 8, c_lo + nch);        // channels of this slab
+	double* mine = R.partials + ((size_t)n * gridDim.x + blockIdx.x) * groups * 2;
+	for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+		const int g_lo = max(g * cpg, c_lo), g_hi = min((g + 1) * cpg, c_hi);
+		double a = 0.0, b = 0.0;
+		for (int c = g_lo; c < g_hi; ++c) { a += chs[(c - c_lo) * 2]; b += chs[(c - c_lo) * 2 + 1]; }
+		mine[g * 2] = a; mine[g * 2 + 1] = b;
+	}
+	__threadfence();
+	__syncthreads();
+	if (threadIdx.x == 0) s_last = (atomicAdd(&R.counters[n], 1u) == gridDim.x - 1) ? 1u : 0u;
+	__syncthreads();
+	if (!s_last) return;
+	__threadfence();
+	const double* all = R.partials + (size_t)n * gridDim.x * groups * 2;
+	double* parts = chs + (size_t)nch * 2;                       // [4][groups * 2]
+	const int npair = groups * 2;
+	for (int i = threadIdx.x; i < npair * 4; i += blockDim.x) {   // (part, pair): blocks part, part + 4, ... in order
+		const int part = i / npair, pair = i - part * npair;
+		double a = 0.0;
+		for (unsigned bb = part; bb < gridDim.x; bb += 4) a += all[(size_t)bb * npair + pair];
+		parts[i] = a;
+	}
+	__syncthreads();
+	for (int pair = threadIdx.x; pair < npair; pair += blockDim.x)
+		R.stats[(size_t)n * npair + pair] = ((parts[pair] + parts[npair + pair]) + parts[2 * npair + pair]) + parts[3 * npair + pair];
+	if (threadIdx.x == 0) R.counters[n] = 0;                    // ready for the next run even without the memset
+}
+
 // ------------------------------------------------------------------ GroupNorm (+affine, +SiLU), channels-last f16
 // (mlblock_nn.c:78-103 + ggml_silu_inplace :136,147). Reference statistics are double sums; here
 // per-thread f32 partials over <= 64 elements are combined in double.
@@ -446,21 +506,20 @@ void k_gemm_simt(cudaStream_t s, const View& c, const View& a, const View& b, bo
 // double-precision statistics in global memory.
 template <typename T>
 __global__ void gn_stats_kernel(const T* __restrict__ x, long long HW, int C, int cpg, int groups,
-	long long img_stride, long long pix_stride, double* __restrict__ stats, int pix_per_block, int slab_chunks, int nslabs)
+	long long img_stride, long long pix_stride, GnRed R, int pix_per_block, int slab_chunks, int nslabs)
 {
-	extern __shared__ float sm[];  // [groups][2]
+	extern __shared__ __align__(16) float sm[];
 	const int n = blockIdx.y;
 	const int tile = blockIdx.x / nslabs, slab = blockIdx.x - tile * nslabs;
-	for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sm[i] = 0.f;
-	__syncthreads();
 	const int chunks = C / 8;
 	const int ch = slab * slab_chunks + (int)(threadIdx.x % slab_chunks);
 	const int plane = threadIdx.x / slab_chunks, planes = blockDim.x / slab_chunks;
 	const long long p0 = (long long)tile * pix_per_block, p1 = min(HW, p0 + pix_per_block);
-	if (plane < planes && ch < chunks) {
-		float su[8], sq[8];
-		#pragma unroll
-		for (int j = 0; j < 8; ++j) { su[j] = 0.f; sq[j] = 0.f; }
+	float su[8], sq[8];
+	#pragma unroll
+	for (int j = 0; j < 8; ++j) { su[j] = 0.f; sq[j] = 0.f; }
+	const bool active = plane < planes && ch < chunks;
+	if (active) {
 		const T* base = x + n * img_stride + ch * 8;
 		for (long long p = p0 + plane; p < p1; p += planes) {
 			const T* ptr = base + p * pix_stride;
@@ -477,19 +536,8 @@ __global__ void gn_stats_kernel(const T* __restrict__ x, long long HW, int C, in
 			#pragma unroll
 			for (int j = 0; j < 8; ++j) { su[j] += v[j]; sq[j] += v[j] * v[j]; }
 		}
-		int g = (ch * 8) / cpg;
-		float a = 0.f, b = 0.f;
-		#pragma unroll
-		for (int j = 0; j < 8; ++j) {
-			int gj = (ch * 8 + j) / cpg;
-			if (gj != g) { atomicAdd(&sm[g * 2], a); atomicAdd(&sm[g * 2 + 1], b); a = 0.f; b = 0.f; g = gj; }
-			a += su[j]; b += sq[j];
-		}
-		atomicAdd(&sm[g * 2], a); atomicAdd(&sm[g * 2 + 1], b);
 	}
-	__syncthreads();
-	for (int i = threadIdx.x; i < groups * 2; i += blockDim.x)
-		if (sm[i] != 0.f) atomicAdd(&stats[(long long)n * groups * 2 + i], (double)sm[i]);
+	gn_block_finish(su, sq, active, (int)(threadIdx.x % slab_chunks), plane, planes, slab, slab_chunks, chunks, cpg, groups, n, R, sm);
 }
 
 template <typename TI, typename TO>
@@ -566,21 +614,20 @@ constexpr int GN_BLOCKS_PER_SM = 5;      // both fast kernels are compiled for 5
 
 __global__ void __launch_bounds__(256, GN_BLOCKS_PER_SM)
 gn_stats_fast_kernel(const __half* __restrict__ x, long long HW, int C, int cpg, int groups,
-	long long img_stride, long long pix_stride, double* __restrict__ stats, int pix_per_block, int slab_chunks, int nslabs)
+	long long img_stride, long long pix_stride, GnRed R, int pix_per_block, int slab_chunks, int nslabs)
 {
-	extern __shared__ float sm[];  // [groups][2]
+	extern __shared__ __align__(16) float sm[];
 	const int n = blockIdx.y;
 	const int tile = blockIdx.x / nslabs, slab = blockIdx.x - tile * nslabs;
-	for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sm[i] = 0.f;
-	__syncthreads();
 	const int chunks = C / 8;
 	const int ch = slab * slab_chunks + (int)(threadIdx.x % slab_chunks);
 	const int plane = threadIdx.x / slab_chunks, planes = blockDim.x / slab_chunks;
 	const long long p0 = (long long)tile * pix_per_block, p1 = min(HW, p0 + pix_per_block);
-	if (ch < chunks) {
-		float su[8], sq[8];
-		#pragma unroll
-		for (int j = 0; j < 8; ++j) { su[j] = 0.f; sq[j] = 0.f; }
+	float su[8], sq[8];
+	#pragma unroll
+	for (int j = 0; j < 8; ++j) { su[j] = 0.f; sq[j] = 0.f; }
+	const bool active = ch < chunks;
+	if (active) {
 		const __half* base = x + n * img_stride + ch * 8;
 		long long p = p0 + plane;
 		for (; p + 3 * planes < p1; p += 4 * planes) {
@@ -597,19 +644,8 @@ gn_stats_fast_kernel(const __half* __restrict__ x, long long HW, int C, int cpg,
 			#pragma unroll
 			for (int j = 0; j < 8; ++j) { su[j] += v[j]; sq[j] = fmaf(v[j], v[j], sq[j]); }
 		}
-		int g = (ch * 8) / cpg;
-		float a = 0.f, b = 0.f;
-		#pragma unroll
-		for (int j = 0; j < 8; ++j) {
-			int gj = (ch * 8 + j) / cpg;
-			if (gj != g) { atomicAdd(&sm[g * 2], a); atomicAdd(&sm[g * 2 + 1], b); a = 0.f; b = 0.f; g = gj; }
-			a += su[j]; b += sq[j];
-		}
-		atomicAdd(&sm[g * 2], a); atomicAdd(&sm[g * 2 + 1], b);
 	}
-	__syncthreads();
-	for (int i = threadIdx.x; i < groups * 2; i += blockDim.x)
-		if (sm[i] != 0.f) atomicAdd(&stats[(long long)n * groups * 2 + i], (double)sm[i]);
+	gn_block_finish(su, sq, active, (int)(threadIdx.x % slab_chunks), plane, planes, slab, slab_chunks, chunks, cpg, groups, n, R, sm);
 }
 
 // x * sigmoid(x) = x * (0.5 + 0.5 tanh(x / 2)): one MUFU op per element (tanh.approx) instead of ex2 + rcp
@@ -743,8 +779,45 @@ static void gn_small_launch(cudaStream_t s, bool silu, dim3 grid, const __half* 
 	else gn_small_kernel<false, NV><<<grid, 256, 0, s>>>(x, y, HW, cpg, groups, is, ps, ois, ops, gamma, beta, eps, mul);
 }
 
+static size_t gn_stats_smem(int planes, int slab_chunks, int groups)
+{ return (size_t)planes * slab_chunks * 8 * 2 * sizeof(float) + (size_t)slab_chunks * 8 * 2 * sizeof(double) + (size_t)4 * groups * 2 * sizeof(double); }
+
+// launch geometry of the statistics pass (shared with the planner's scratch sizing)
+struct GnGeom { int threads, planes, slab_chunks, nslabs, pix_per_block; unsigned grid_x; };
+static GnGeom gn_geom(long long HW, int C, long long N, bool fast)
+{
+	GnGeom g;
+	const int chunks = C / 8;
+	if (fast) {
+		g.nslabs = (chunks + 255) / 256; g.slab_chunks = (chunks + g.nslabs - 1) / g.nslabs;
+		g.planes = std::max(1, 256 / g.slab_chunks); g.threads = g.slab_chunks * g.planes;
+		// One exact wave: 148 SMs x GN_BLOCKS_PER_SM resident blocks share the pixels evenly (no tail wave, every SM equally
+		// loaded); small tensors get one pixel row of `planes` pixels per block at least.
+		const long long target = 148LL * GN_BLOCKS_PER_SM;
+		const long long tiles_want = std::max<long long>(1, target / std::max<long long>(1, N * g.nslabs));
+		long long ppb = (HW + tiles_want - 1) / tiles_want;
+		ppb = std::max<long long>(g.planes, (ppb + g.planes - 1) / g.planes * g.planes);
+		g.pix_per_block = (int)std::min<long long>(ppb, 1 << 30);
+	} else {
+		g.threads = 256;
+		g.slab_chunks = std::min(chunks, 64); g.nslabs = (chunks + g.slab_chunks - 1) / g.slab_chunks;
+		g.planes = g.threads / g.slab_chunks;
+		g.pix_per_block = g.planes * 16;                  // 16 pixels per thread
+		if (HW * N * g.nslabs < 148LL * 4 * g.pix_per_block) g.pix_per_block = g.planes * 4;   // small tensors: more, smaller blocks
+	}
+	g.grid_x = (unsigned)(((HW + g.pix_per_block - 1) / g.pix_per_block) * g.nslabs);
+	return g;
+}
+
+size_t k_groupnorm_scratch_bytes(long long HW, int C, long long N, int groups)
+{
+	const unsigned gx = std::max(gn_geom(HW, C, N, true).grid_x, gn_geom(HW, C, N, false).grid_x);
+	return (size_t)N * gx * groups * 2 * sizeof(double);
+}
+
+// stats: [N][groups][2] doubles followed by N 32-bit block counters (zeroed before the run); scratch: k_groupnorm_scratch_bytes
 void k_groupnorm(cudaStream_t s, const View& dst, const View& src, const float* gamma, const float* beta,
-	int groups, float eps, bool silu, double* stats)
+	int groups, float eps, bool silu, double* stats, double* scratch)
 {
 	int C = (int)src.ne[2]; long long W = src.ne[0], H = src.ne[1], N = src.ne[3], HW = W * H;
 	int cpg = (C + groups - 1) / groups;
@@ -766,19 +839,14 @@ void k_groupnorm(cudaStream_t s, const View& dst, const View& src, const float* 
 			g_stats.kernel_launches++;
 			return;
 		}
-		const int chunks = C / 8;
-		const int nslabs = (chunks + 255) / 256, slab_chunks = (chunks + nslabs - 1) / nslabs;
-		const int planes = std::max(1, 256 / slab_chunks), threads = slab_chunks * planes;
-		// One exact wave: 148 SMs x GN_BLOCKS_PER_SM resident blocks share the pixels evenly (no tail wave, every SM equally
-		// loaded); small tensors get one pixel row of `planes` pixels per block at least.
-		const long long target = 148LL * GN_BLOCKS_PER_SM;
-		const long long tiles_want = std::max<long long>(1, target / std::max<long long>(1, N * nslabs));
-		long long ppb = (HW + tiles_want - 1) / tiles_want;
-		ppb = std::max<long long>(planes, (ppb + planes - 1) / planes * planes);
-		const int pix_per_block = (int)std::min<long long>(ppb, 1 << 30);
-		dim3 grid((unsigned)(((HW + pix_per_block - 1) / pix_per_block) * nslabs), (unsigned)N);
+		const GnGeom G = gn_geom(HW, C, N, true);
+		const int slab_chunks = G.slab_chunks, nslabs = G.nslabs, threads = G.threads, pix_per_block = G.pix_per_block;
+		dim3 grid(G.grid_x, (unsigned)N);
 		const size_t smem = groups * 2 * sizeof(float);
-		gn_stats_fast_kernel<<<grid, threads, smem, s>>>((const __half*)src.ptr, HW, C, cpg, groups, src.st[3], src.st[0], stats, pix_per_block, slab_chunks, nslabs);
+		const GnRed R = { stats, scratch, reinterpret_cast<unsigned*>(stats + (size_t)N * groups * 2) };
+		static bool attr = false;
+		if (!attr) { CUDA_CHECK(cudaFuncSetAttribute(gn_stats_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
+		gn_stats_fast_kernel<<<grid, threads, gn_stats_smem(G.planes, slab_chunks, groups), s>>>((const __half*)src.ptr, HW, C, cpg, groups, src.st[3], src.st[0], R, pix_per_block, slab_chunks, nslabs);
 		if (silu)
 			gn_apply_fast_kernel<true><<<grid, threads, smem, s>>>((const __half*)src.ptr, (__half*)dst.ptr, HW, C, cpg, groups, src.st[3], src.st[0],
 				dst.st[3], dst.st[0], gamma, beta, stats, eps, pix_per_block, slab_chunks, nslabs);
@@ -788,18 +856,16 @@ void k_groupnorm(cudaStream_t s, const View& dst, const View& src, const float* 
 		g_stats.kernel_launches += 2;
 		return;
 	}
-	int threads = 256;
-	int chunks = C / 8;
-	int slab_chunks = std::min(chunks, 64), nslabs = (chunks + slab_chunks - 1) / slab_chunks;
-	int planes = threads / slab_chunks;
-	int pix_per_block = planes * 16;                  // 16 pixels per thread
-	if (HW * N * nslabs < 148LL * 4 * pix_per_block) pix_per_block = planes * 4;   // small tensors: more, smaller blocks
-	dim3 g1((unsigned)(((HW + pix_per_block - 1) / pix_per_block) * nslabs), (unsigned)N);
+	const GnGeom G = gn_geom(HW, C, N, false);
+	const int threads = G.threads, slab_chunks = G.slab_chunks, nslabs = G.nslabs, pix_per_block = G.pix_per_block;
+	dim3 g1(G.grid_x, (unsigned)N);
 	size_t smem = groups * 2 * sizeof(float);
+	const GnRed R = { stats, scratch, reinterpret_cast<unsigned*>(stats + (size_t)N * groups * 2) };
+	const size_t smem1 = gn_stats_smem(G.planes, slab_chunks, groups);
 	if (src.dt == DT_F16)
-		gn_stats_kernel<__half><<<g1, threads, smem, s>>>((const __half*)src.ptr, HW, C, cpg, groups, src.st[3], src.st[0], stats, pix_per_block, slab_chunks, nslabs);
+		gn_stats_kernel<__half><<<g1, threads, smem1, s>>>((const __half*)src.ptr, HW, C, cpg, groups, src.st[3], src.st[0], R, pix_per_block, slab_chunks, nslabs);
 	else
-		gn_stats_kernel<float><<<g1, threads, smem, s>>>((const float*)src.ptr, HW, C, cpg, groups, src.st[3], src.st[0], stats, pix_per_block, slab_chunks, nslabs);
+		gn_stats_kernel<float><<<g1, threads, smem1, s>>>((const float*)src.ptr, HW, C, cpg, groups, src.st[3], src.st[0], R, pix_per_block, slab_chunks, nslabs);
 	long long total = HW * (C / 8);
 	dim3 g2((unsigned)std::min<long long>((total + threads - 1) / threads, 148 * 8), (unsigned)N);
 	if (src.dt == DT_F16 && dst.dt == DT_F16)

@@ -50,15 +50,20 @@ def gen_unet(name):
     ctx.setup()
     sigma0 = float(L.unet_t_to_sigma(C.addressof(C.c_char.in_dll(L, {"sd1": "g_unet_sd1", "sd2": "g_unet_sd2", "sdxl": "g_unet_sdxl"}[c["model"]])), 999.0 * c["f_t_ini"]))
     lat = G.unet_inputs(name)[0]
-    outs, xs = [], []
+    outs, xs, outs_u = [], [], []
     for i in range(c["n"]):
         t0 = time.time()
-        outs.append(G.unet_step(ctx, api, name, [i], seed_set)[0])
+        if c["cfg"] > 1:      # the two halves separately (cfg 1 each): the per-evaluation outputs; the test forms the combine
+            outs.append(G.unet_step(ctx, api, name, [i], seed_set, half="cond")[0])
+            outs_u.append(G.unet_step(ctx, api, name, [i], seed_set, half="ncond")[0])
+        else:
+            outs.append(G.unet_step(ctx, api, name, [i], seed_set)[0])
         xs.append(lat[i] + sigma0 * randn(42 + i, lat[i].size).reshape(lat[i].shape))
         print("  %s image %d: %.1f s" % (name, i, time.time() - t0), flush=True)
     ctx.close()
     out, x = np.stack(outs), np.stack(xs).astype(np.float32)
-    np.savez_compressed(os.path.join(G.GOLD, name + ".npz"), out=out, x=x, sigma0=np.float32(sigma0))
+    extra = {"out_u": np.stack(outs_u)} if outs_u else {}
+    np.savez_compressed(os.path.join(G.GOLD, name + ".npz"), out=out, x=x, sigma0=np.float32(sigma0), **extra)
     dx = (x - out) / sigma0
     print(name, "sigma0 %.4f  |dx| max %.3f rms %.3f" % (sigma0, np.abs(dx).max(), np.sqrt((dx ** 2).mean())), flush=True)
 
