@@ -35,7 +35,7 @@ constexpr int A_TMEM_COLS = 512;
 constexpr int A_MAX_STAGES = 4;
 
 struct AttnParams {
-	int d, d16, dchunks, nq, nk, H, B, stages, nblk, pingpong, sep_p, dual, npoly;
+	int d, d16, dchunks, nq, nk, H, B, stages, nblk, pingpong, sep_p, dual, npoly, split;
 	float scale_log2;
 	void* o; long long so_t, so_h, so_b;
 	long long* trace;     // debug timeline (tools/attn_trace.cu); null in production
@@ -398,6 +398,281 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 }
 
 
+
+// ------------------------------------------------------------------ heads up to 64 wide: key-split form
+// For d <= 64 the exponentials bound the kernel (MUFU.EX2: 16 per clock and SM, i.e. 1024 clk per 128 x 128 score tile against
+// 2 * (d16/16) * 64 clk of MMA). The one-row-per-thread forms above keep ONE (ping-pong) or TWO (dual) softmax warps per SM
+// sub-partition, and each of them spends half of its time outside the exponential pass (waiting for the products, loading
+// scores twice, the maximum pass): the MUFU pipe idles 48 % of the time (ncu, profiles/r1_ncu_attention.md).
+// Here a CTA still owns one tile of 128 query rows, but EIGHT softmax warps work on every key block: warps 0..3 take the
+// keys [0, 64) of the block, warps 4..7 the keys [64, 128). The two halves never talk to each other inside the loop:
+//   * each half keeps its own running maximum and sum per row and its own output accumulator in tensor memory
+//     (O_a, O_b: the PV product of a block is issued as two K = 64 products), like a split-KV decode;
+//   * a thread reads its 64 scores ONCE (two tcgen05.ld), keeps them in registers for the maximum and the exponentials,
+//     and writes the f16 probabilities over the first half of its own score columns;
+//   * the halves are merged in the epilogue through 2 KB of shared memory: O = (O_a w_a + O_b w_b) / (l_a w_a + l_b w_b).
+// Two such CTAs share an SM (256 tensor-memory columns, <= 113 KB of shared memory each): four softmax warps per SM
+// sub-partition keep the MUFU pipe fed while the others wait, load or pack.
+template <int N_POLY>
+__global__ void __launch_bounds__(320, 2)
+attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+	const AttnParams p)
+{
+	extern __shared__ __align__(1024) uint8_t smem_raw[];
+	uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+	const int tile_bytes = p.dchunks * CHUNK_BYTES;       // dchunks == 1 here (d <= 64)
+	uint8_t* sQ = smem;
+	uint8_t* sK = sQ + tile_bytes;
+	uint8_t* sV = sK + (size_t)p.stages * tile_bytes;
+	uint64_t* bars = (uint64_t*)(sV + (size_t)p.stages * tile_bytes);
+	uint64_t* q_full = bars;                        // [1]
+	uint64_t* k_full = q_full + 1;                  // [stages]
+	uint64_t* k_empty = k_full + A_MAX_STAGES;
+	uint64_t* v_full = k_empty + A_MAX_STAGES;
+	uint64_t* v_empty = v_full + A_MAX_STAGES;
+	uint64_t* s_full = v_empty + A_MAX_STAGES;      // [1]   QK done
+	uint64_t* p_full = s_full + 1;                  // [2]   probabilities of a half written (128 arrivals)
+	uint64_t* pv_full = p_full + 2;                 // [2]   PV of a half done
+	uint32_t* tmem_slot = (uint32_t*)(pv_full + 2);
+	float2* exch = (float2*)(tmem_slot + 2);        // [2 halves][128 rows] (running maximum, running sum)
+
+	const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
+	const int q0 = blockIdx.x * AQ, h = blockIdx.y, b = blockIdx.z;
+	constexpr uint32_t O_BASE = 128, O_STRIDE = 64;   // TMEM: S at 0 (P_a over columns [0,32), P_b over [64,96)), O_a at 128, O_b at 192
+	constexpr int W_TMA = 8, W_MMA = 9;
+
+	if (threadIdx.x == 0) {
+		tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+		for (int s = 0; s < p.stages; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+		mbar_init(q_full, 1); mbar_init(s_full, 1);
+		for (int t = 0; t < 2; ++t) { mbar_init(&p_full[t], 128); mbar_init(&pv_full[t], 1); }
+		fence_barrier_init();
+	}
+	if (warp == W_MMA) tmem_alloc(tmem_slot, 256);
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = uniform_u32(*tmem_slot);
+
+	if (warp == W_TMA) {
+		if (lane == 0) {
+			mbar_expect_tx(q_full, tile_bytes);
+			tma_load_4d(sQ, &tmQ, q_full, 0, q0, h, b);
+			for (int j = 0; j < p.nblk; ++j) {
+				const int s = j % p.stages; const uint32_t ph = (uint32_t)(j / p.stages) & 1;
+				mbar_wait(&k_empty[s], ph ^ 1);
+				mbar_expect_tx(&k_full[s], tile_bytes);
+				tma_load_4d(sK + (size_t)s * tile_bytes, &tmK, &k_full[s], 0, j * AK, h, b);
+				mbar_wait(&v_empty[s], ph ^ 1);
+				mbar_expect_tx(&v_full[s], tile_bytes);
+				tma_load_4d(sV + (size_t)s * tile_bytes, &tmV, &v_full[s], 0, j * AK, h, b);
+			}
+		}
+	} else if (warp == W_MMA) {
+		const uint32_t idesc_qk = make_idesc_f16(AQ, AK, 0, 0);
+		const uint32_t idesc_pv = make_idesc_f16(AQ, p.d16, 0, 1);     // A = P (TMEM), B = V MN-major ([key][d], d contiguous)
+		const uint64_t qdesc0 = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+		const uint64_t kdesc0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+		const uint64_t vdesc0 = make_smem_desc_sw128(smem_u32(sV), CHUNK_BYTES, 1024);
+		const uint32_t tile16 = (uint32_t)tile_bytes >> 4;
+		const int nk16 = p.d16 >> 4;
+		auto issue_qk = [&](int j) {
+			const int s = j % p.stages;
+			mbar_wait(&k_full[s], (uint32_t)(j / p.stages) & 1);
+			tc_fence_after();
+			if (elect_one()) {
+				const uint64_t bd = kdesc0 + (uint64_t)(s * tile16);
+				#pragma unroll
+				for (int kk = 0; kk < 4; ++kk)
+					if (kk < nk16) umma_f16(tmem_base, qdesc0 + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc_qk, kk ? 1u : 0u);
+				umma_commit(s_full);
+				umma_commit(&k_empty[s]);
+			}
+			__syncwarp();
+		};
+		mbar_wait(q_full, 0);
+		issue_qk(0);
+		for (int j = 0; j < p.nblk; ++j) {
+			const int s = j % p.stages;
+			const int valid = min(AK, p.nk - j * AK);
+			mbar_wait(&v_full[s], (uint32_t)(j / p.stages) & 1);
+			#pragma unroll
+			for (int hf = 0; hf < 2; ++hf) {
+				mbar_wait(&p_full[hf], (uint32_t)j & 1);
+				tc_fence_after();
+				if (elect_one()) {
+					// V tile: rows = keys (128 B each), 16 keys further = +16 * 128 B; the second half starts 64 keys in.
+					// P in tensor memory: 16 keys = 8 packed 32-bit columns, half b's probabilities start at column 64.
+					const uint64_t bd = vdesc0 + (uint64_t)(s * tile16) + (uint64_t)(hf * 512);
+					const uint32_t td = tmem_base + O_BASE + hf * O_STRIDE, ta = tmem_base + hf * 64;
+					const int nkk = (min(64, max(0, valid - hf * 64)) + 15) >> 4;
+					#pragma unroll
+					for (int kk = 0; kk < 4; ++kk)
+						if (kk < nkk) umma_f16_ts(td, ta + kk * 8, bd + (uint64_t)(kk * 128), idesc_pv, (j | kk) ? 1u : 0u);
+					umma_commit(&pv_full[hf]);
+					if (hf == 1) umma_commit(&v_empty[s]);
+				}
+				__syncwarp();
+			}
+			if (j + 1 < p.nblk) issue_qk(j + 1);        // in order after both products: S / P may be overwritten
+		}
+	} else {
+		// ===== softmax: warp = quarter (TMEM lanes) + 4 * half (key columns); one (row, half) per thread =====
+		const int hf = warp >> 2, quarter = warp & 3;
+		const int r = quarter * 32 + lane;
+		const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+		const uint32_t ts = tmem_base + lane_off + hf * 64;                      // my 64 scores; the probabilities go over their first 32 columns
+		const uint32_t to = tmem_base + O_BASE + hf * O_STRIDE + lane_off;       // my half's output accumulator of this row
+		const float sl2 = p.scale_log2;
+		float m = -INFINITY, l = 0.f;
+		bool first = true;
+
+		auto block = [&](int j, auto full_tag) {
+			constexpr bool FULL = decltype(full_tag)::value;
+			const int valid = FULL ? 64 : min(64, max(0, p.nk - j * AK - hf * 64));      // valid keys of my half
+			mbar_wait(s_full, (uint32_t)j & 1);
+			tc_fence_after();
+			uint32_t va[32], vb[32];
+			if (!FULL && valid <= 0) {                                           // nothing of this block belongs to my half
+				#pragma unroll
+				for (int i = 0; i < 16; ++i) va[i] = 0u;
+				tmem_st16(ts, va); tmem_st16(ts + 16, va);
+				tmem_st_wait(); tc_fence_before(); mbar_arrive(&p_full[hf]);
+				return;
+			}
+			tmem_ld32(ts, va); tmem_ld32(ts + 32, vb);
+			tmem_ld_wait();
+			float mx4[4] = { -INFINITY, -INFINITY, -INFINITY, -INFINITY };
+			if (FULL) {
+				#pragma unroll
+				for (int i = 0; i < 32; i += 8) {
+					mx4[0] = max3f(mx4[0], __uint_as_float(va[i]), __uint_as_float(va[i + 1]));
+					mx4[1] = max3f(mx4[1], __uint_as_float(va[i + 2]), __uint_as_float(va[i + 3]));
+					mx4[2] = max3f(mx4[2], __uint_as_float(va[i + 4]), __uint_as_float(va[i + 5]));
+					mx4[3] = max3f(mx4[3], __uint_as_float(va[i + 6]), __uint_as_float(va[i + 7]));
+					mx4[0] = max3f(mx4[0], __uint_as_float(vb[i]), __uint_as_float(vb[i + 1]));
+					mx4[1] = max3f(mx4[1], __uint_as_float(vb[i + 2]), __uint_as_float(vb[i + 3]));
+					mx4[2] = max3f(mx4[2], __uint_as_float(vb[i + 4]), __uint_as_float(vb[i + 5]));
+					mx4[3] = max3f(mx4[3], __uint_as_float(vb[i + 6]), __uint_as_float(vb[i + 7]));
+				}
+			} else {
+				#pragma unroll
+				for (int i = 0; i < 32; ++i) {
+					if (i < valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(va[i]));
+					if (32 + i < valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(vb[i]));
+				}
+			}
+			const float m_blk = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sl2;
+			// Lazy rescaling (as above): keep the old maximum while the block maximum exceeds it by < 2^8.
+			if (first) { m = m_blk; first = false; }
+			else {
+				const bool need = m_blk > m + 8.0f;
+				if (__any_sync(0xffffffffu, need)) {
+					const float m_new = need ? m_blk : m;
+					const float corr = ex2_approx(m - m_new);
+					m = m_new;
+					l *= corr;
+					mbar_wait(&pv_full[hf], (uint32_t)(j - 1) & 1);     // my half's PV products so far have landed in O
+					tc_fence_after();
+					#pragma unroll
+					for (int c0 = 0; c0 < 64; c0 += 16) {
+						if (c0 < p.d16) {
+							uint32_t o[16];
+							tmem_ld16(to + c0, o);
+							tmem_ld_wait();
+							#pragma unroll
+							for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+							tmem_st16(to + c0, o);
+						}
+					}
+				}
+			}
+			const float mneg = -m;
+			float rs4[4] = { 0.f, 0.f, 0.f, 0.f };
+			auto exps = [&](uint32_t* v, int c) {
+				#pragma unroll
+				for (int i = 0; i < 32; ++i) {
+					const float xs = fmaf(__uint_as_float(v[i]), sl2, mneg);
+					float e = (i & 7) < N_POLY ? ex2_poly(xs) : ex2_approx(xs);
+					if (!FULL) { if (c * 32 + i >= valid) e = 0.f; }
+					v[i] = __float_as_uint(e);
+				}
+			};
+			auto finish = [&](const uint32_t* v, int c) {
+				uint32_t packed[16];
+				#pragma unroll
+				for (int i = 0; i < 32; i += 2) {
+					const float p0 = __uint_as_float(v[i]), p1 = __uint_as_float(v[i + 1]);
+					rs4[(i >> 1) & 3] += p0 + p1;
+					__half2 hh = __floats2half2_rn(p0, p1);
+					packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+				}
+				tmem_st16(ts + c * 16, packed);
+			};
+			exps(va, 0); exps(vb, 1);
+			finish(va, 0); finish(vb, 1);
+			l += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+			tmem_st_wait();
+			tc_fence_before();
+			mbar_arrive(&p_full[hf]);
+		};
+		const int nfull = p.nk / AK;      // a partial block can only be the last one
+		for (int j = 0; j < nfull; ++j) block(j, std::true_type{});
+		if (nfull < p.nblk) block(nfull, std::false_type{});
+
+		// epilogue: merge the halves. Every thread publishes (m, l) of its (row, half), then takes the 16-column chunks
+		// c with (c & 1) == half of BOTH accumulators of its row.
+		mbar_wait(&pv_full[0], (uint32_t)(p.nblk - 1) & 1);
+		mbar_wait(&pv_full[1], (uint32_t)(p.nblk - 1) & 1);
+		tc_fence_after();
+		exch[hf * 128 + r] = make_float2(m, l);
+		named_bar_sync(1, 256);
+		const float2 oth = exch[(hf ^ 1) * 128 + r];
+		const float M = fmaxf(m, oth.x);
+		const float w_me = first ? 0.f : ex2_approx(m - M), w_ot = (oth.x == -INFINITY) ? 0.f : ex2_approx(oth.x - M);
+		const float L = l * w_me + oth.y * w_ot;
+		const float inv = L > 0.f ? 1.0f / L : 0.f;
+		const float s_me = w_me * inv, s_ot = w_ot * inv;
+		const uint32_t to_ot = tmem_base + O_BASE + (hf ^ 1) * O_STRIDE + lane_off;
+		const long long tok = (long long)q0 + r;
+		__half* op = (__half*)p.o + tok * p.so_t + (long long)h * p.so_h + (long long)b * p.so_b;
+		const bool vec = ((((uintptr_t)op) & 15) == 0);
+		#pragma unroll
+		for (int c = 0; c < 4; ++c) {
+			const int c0 = c * 16;
+			if ((c & 1) == hf && c0 < p.d16) {
+				uint32_t oa[16], ob[16];
+				tmem_ld16(to + c0, oa); tmem_ld16(to_ot + c0, ob);
+				tmem_ld_wait();
+				if (tok < p.nq) {
+					float o[16];
+					#pragma unroll
+					for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(oa[i]) * s_me + __uint_as_float(ob[i]) * s_ot;
+					#pragma unroll
+					for (int h8 = 0; h8 < 16; h8 += 8) {
+						const int cc = c0 + h8;
+						if (cc < p.d) {
+							if (vec && cc + 8 <= p.d) {
+								uint4 o4; __half2* hp = reinterpret_cast<__half2*>(&o4);
+								#pragma unroll
+								for (int i = 0; i < 4; ++i) hp[i] = __floats2half2_rn(o[h8 + 2 * i], o[h8 + 2 * i + 1]);
+								*reinterpret_cast<uint4*>(op + cc) = o4;
+							} else {
+								#pragma unroll
+								for (int i = 0; i < 8; ++i) if (cc + i < p.d) op[cc + i] = __float2half_rn(o[h8 + i]);
+							}
+						}
+					}
+				}
+			}
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == W_MMA) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
+
 // ------------------------------------------------------------------ single key block (cross-attention, nk <= 128)
 // The text context of a cross-attention has 77 keys (unet.c:110-145): one key block. With one (pair of) query tile(s)
 // per CTA such a launch is a chain of latencies -- load, QK^T, softmax, PV, store -- that nothing overlaps, ~6 us per
@@ -650,11 +925,13 @@ AttnTC* attn_tc_prepare(const View& o, const View& q, const View& k, const View&
 	p.stages = std::max(1, std::min(p.nblk, A_MAX_STAGES));
 	// heads up to 64 wide: one tile per CTA, two CTAs per SM (measured 7-12 % faster than two ping-pong tiles in one CTA)
 	{ const char* e = getenv("GGML_B200_ATTN_DUAL"); p.dual = (e ? atoi(e) : 1) && p.d16 <= 64 && p.nblk > 1; }
+	// key-split form of the dual layout (eight softmax warps per CTA): default for heads up to 64 wide
+	{ const char* e = getenv("GGML_B200_ATTN_SPLIT"); p.split = p.dual && (e ? atoi(e) : 1); }
 	const int nt = (p.d16 > 128 || p.dual) ? 1 : 2;
 	if (p.dual) p.stages = std::min(p.stages, 2);             // two CTAs per SM: <= 113 KB each
 	auto total = [&]() { return tile * (nt + 2 * p.stages) + 1024 + 512; };
 	while (total() > 220 * 1024 && p.stages > 1) p.stages--;
-	a->smem = total();
+	a->smem = total() + (p.split ? 2048 : 0);       // + the (maximum, sum) exchange of the key-split form
 	a->grid = dim3((unsigned)((p.nq + nt * AQ - 1) / (nt * AQ)), (unsigned)p.H, (unsigned)p.B);
 	{
 		// one key block (cross-attention): CTAs walk the query tiles of their (head, image); as many CTAs per (head, image)
@@ -687,6 +964,9 @@ void attn_tc_launch(cudaStream_t s, AttnTC* a)
 		CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute((attn_tc_kernel<64, 1, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute((attn_tc_kernel<64, 1, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute(attn_split_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute(attn_split_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute(attn_split_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute(attn_kv1_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute(attn_kv1_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		attr_set = true;
@@ -694,6 +974,13 @@ void attn_tc_launch(cudaStream_t s, AttnTC* a)
 	if (a->kv1) {
 		if (a->p.d16 <= 64) attn_kv1_kernel<64><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
 		else attn_kv1_kernel<128><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+		g_stats.kernel_launches++;
+		return;
+	}
+	if (a->p.split) {
+		if (a->p.npoly == 2) attn_split_kernel<2><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+		else if (a->p.npoly == 1) attn_split_kernel<1><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+		else attn_split_kernel<0><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
 		g_stats.kernel_launches++;
 		return;
 	}

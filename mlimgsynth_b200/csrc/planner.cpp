@@ -449,7 +449,12 @@ bool Builder::try_attention(ggml_tensor* t)
 		o.ne[0] = pv->ne[0]; o.ne[1] = pv->ne[1]; o.ne[2] = pv->ne[2]; o.ne[3] = pv->ne[3];
 		o.st[0] = 1; o.st[2] = o.ne[0]; o.st[1] = o.ne[0] * o.ne[2]; o.st[3] = o.st[1] * o.ne[1];
 		o.buf = new_buf(BUF_ARENA, (size_t)o.numel() * 2);
-		int64_t ne_s[4] = { nk, nq, 1, 1 };
+		// The score block is bounded: queries are processed in chunks of <= 2^26 / nk rows (S chunk <= 256 MB f32 + 128 MB
+		// f16 probabilities, reused by every chunk, head and image), so the footprint no longer grows with nq * nk
+		// (16384 tokens at 1024x1024: 1.6 GB before, 0.4 GB now; the untiled 2048x2048 decode: 25 GB -> 0.4 GB).
+		int64_t qc = std::max<int64_t>(128, ((int64_t)1 << 26) / nk / 128 * 128);
+		if (qc > nq) qc = nq;
+		int64_t ne_s[4] = { nk, qc, 1, 1 };
 		PT S = new_pt(DT_F32, ne_s), Pm = new_pt(DT_F16, ne_s);
 		int64_t ne_vt[4] = { nk, d, 1, 1 };
 		PT Vt = new_pt(DT_F16, ne_vt);
@@ -458,17 +463,24 @@ bool Builder::try_attention(ggml_tensor* t)
 			qa.off += h * A.st[2] + b * A.st[3]; ka.off += h * Bk.st[2] + b * Bk.st[3];
 			va.off += h * pvv.st[2] + b * pvv.st[3]; oa.off += h * o.st[2] + b * o.st[3];
 			for (PT* x : { &qa, &ka, &va, &oa }) { x->ne[2] = x->ne[3] = 1; }
-			Step g1; g1.kind = S_GEMM_TC; g1.name = "attn_qk";
-			g1.in[0] = qa; g1.in[1] = ka; g1.n_in = 2; g1.out = S;
-			g1.M = nq; g1.N = nk; g1.K = d; g1.lda = A.st[1]; g1.ldb = Bk.st[1]; g1.ldc = nk;
-			P->steps.push_back(g1);
-			Step& sm2 = emit(S_SOFTMAX_F16, "attn_softmax");
-			sm2.out = Pm; sm2.in[0] = S; sm2.n_in = 1; sm2.fparam = scale;
 			copy(Vt, va, "attn_v_transpose");          // [nk, d] view of token-major V -> rows of nk keys per channel
-			Step g2; g2.kind = S_GEMM_TC; g2.name = "attn_pv";
-			g2.in[0] = Pm; g2.in[1] = Vt; g2.n_in = 2; g2.out = oa;
-			g2.M = nq; g2.N = d; g2.K = nk; g2.lda = nk; g2.ldb = nk; g2.ldc = o.st[1];
-			P->steps.push_back(g2);
+			for (int64_t r0 = 0; r0 < nq; r0 += qc) {
+				const int64_t rows = std::min(qc, nq - r0);
+				PT qr = qa, orr = oa, Sr = S, Pr = Pm;
+				qr.off += r0 * A.st[1]; qr.ne[1] = rows;
+				orr.off += r0 * o.st[1]; orr.ne[1] = rows;
+				Sr.ne[1] = rows; Pr.ne[1] = rows;
+				Step g1; g1.kind = S_GEMM_TC; g1.name = "attn_qk";
+				g1.in[0] = qr; g1.in[1] = ka; g1.n_in = 2; g1.out = Sr;
+				g1.M = rows; g1.N = nk; g1.K = d; g1.lda = A.st[1]; g1.ldb = Bk.st[1]; g1.ldc = nk;
+				P->steps.push_back(g1);
+				Step& sm2 = emit(S_SOFTMAX_F16, "attn_softmax");
+				sm2.out = Pr; sm2.in[0] = Sr; sm2.n_in = 1; sm2.fparam = scale;
+				Step g2; g2.kind = S_GEMM_TC; g2.name = "attn_pv";
+				g2.in[0] = Pr; g2.in[1] = Vt; g2.n_in = 2; g2.out = orr;
+				g2.M = rows; g2.N = d; g2.K = nk; g2.lda = nk; g2.ldb = nk; g2.ldc = o.st[1];
+				P->steps.push_back(g2);
+			}
 		}
 		done[t] = done[sc] = done[sm] = true;
 		finish(pv, o);

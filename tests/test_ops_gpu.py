@@ -153,8 +153,11 @@ def test_attn_mhead(ref, eng, nq, nk, d_embed, n_head, mask):
     check(build, ref, eng, BLOCK_TOL)
 
 
-def test_attn_2d_self_vae(ref, eng):
-    check(lambda b: b.attn_2d_self(b.inp(1, 512, 16, 16)), ref, eng, BLOCK_TOL)
+@pytest.mark.parametrize("side", [16, 96])
+def test_attn_2d_self_vae(ref, eng, side):
+    """VAE middle-block attention (vae.c:46-74), one 512-wide head. side 96 = 9216 tokens: the score block exceeds the
+    planner's bound, so the queries run in two chunks (7168 + 2048 rows) through the same buffers."""
+    check(lambda b: b.attn_2d_self(b.inp(1, 512, side, side)), ref, eng, BLOCK_TOL)
 
 
 # ---------------------------------------------------------------- blocks
