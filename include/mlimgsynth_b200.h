@@ -159,6 +159,15 @@ int mlis_b200_vae_tile_plan(MLIS_Ctx* ctx, int lw, int lh, int* n_tiles, int* ti
 int mlis_b200_vae_tiles_decode(MLIS_Ctx* ctx, const MLIS_Tensor* latent, int rank, int world, float* tiles_dev);
 int mlis_b200_vae_tiles_merge(MLIS_Ctx* ctx, int lw, int lh, const float* gathered_dev, int world, int slots_per_worker, MLIS_Tensor* image);
 
+/* Cross-GPU CFG split (opt-in, for fewer images than GPUs; the default batches both halves on one GPU). The reference
+ * evaluates the conditional and the unconditional UNet one after the other (mlimgsynth.c:1578-1583); they only share x and
+ * sigma, so a PAIR of contexts on two GPUs -- same model, options, seed and prompts -- can each evaluate one half
+ * (half 0 = conditional, 1 = unconditional). Once per UNet evaluation the library calls `exchange` with this rank's output
+ * (device pointer, n floats) and a device buffer to fill with the peer's output (a 2-rank all-gather, e.g. NCCL); both ranks
+ * then form the same dx and keep identical sampler states. half < 0 switches the mode off. */
+typedef int (*MLIS_B200_CfgExchange)(void* user, const float* mine_dev, float* other_dev, size_t n);
+int mlis_b200_cfg_split_set(MLIS_Ctx* ctx, int half, MLIS_B200_CfgExchange exchange, void* user);
+
 /* Device pointer of the RGB8 images ([n][h][w][3] bytes) of the last generation / decode, for device-to-device gathers. */
 int mlis_b200_images_device(MLIS_Ctx* ctx, const uint8_t** dev, int* w, int* h, int* n);
 

@@ -23,6 +23,7 @@ TUF_IMAGE, TUF_MASK, TUF_LATENT, TUF_LMASK, TUF_CONDITIONING = 1, 2, 4, 8, 16
 SUBMODEL_CLIP, SUBMODEL_CLIP2 = 4, 5
 OPT_IMAGE, OPT_IMAGE_MASK, OPT_CALLBACK = 20, 21, 30
 CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(MLIS_Progress))
+CFG_EXCHANGE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
 
 _lib = None
 
@@ -184,6 +185,22 @@ class Ctx:
         out = _from_tensor(img)
         self.L.mlis_tensor_free(C.byref(img))
         return out
+
+    def cfg_split(self, half, exchange=None):
+        """Cross-GPU CFG split: this context evaluates CFG half `half` (0 cond, 1 uncond); exchange(mine_ptr, other_ptr, n)
+        must fill the peer's output (device pointers, n floats). half=None switches it off."""
+        if half is None:
+            self._cfg_cb = None
+            return self._chk(self.L.mlis_b200_cfg_split_set(self.h, -1, CFG_EXCHANGE(0), None))
+        def cb(user, mine, other, n):
+            try:
+                exchange(mine, other, n)
+                return 1
+            except Exception as e:      # never let an exception cross the C boundary
+                print("cfg exchange failed:", e)
+                return -1
+        self._cfg_cb = CFG_EXCHANGE(cb)
+        return self._chk(self.L.mlis_b200_cfg_split_set(self.h, half, self._cfg_cb, None))
 
     def images_device(self):
         """(device pointer, n, h, w) of the RGB8 images of the last generation as they lie in HBM."""

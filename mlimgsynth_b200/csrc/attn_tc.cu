@@ -431,9 +431,9 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 	uint64_t* v_full = k_empty + A_MAX_STAGES;
 	uint64_t* v_empty = v_full + A_MAX_STAGES;
 	uint64_t* s_full = v_empty + A_MAX_STAGES;      // [1]   QK done
-	uint64_t* p_full = s_full + 1;                  // [2]   probabilities of a half written (128 arrivals)
-	uint64_t* pv_full = p_full + 2;                 // [2]   PV of a half done
-	uint32_t* tmem_slot = (uint32_t*)(pv_full + 2);
+	uint64_t* p_full = s_full + 1;                  // [1]   probabilities of both halves written (256 arrivals)
+	uint64_t* pv_full = p_full + 1;                 // [1]   both PV products of a block done
+	uint32_t* tmem_slot = (uint32_t*)(pv_full + 1);
 	float2* exch = (float2*)(tmem_slot + 2);        // [2 halves][128 rows] (running maximum, running sum)
 
 	const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
@@ -444,8 +444,7 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 	if (threadIdx.x == 0) {
 		tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
 		for (int s = 0; s < p.stages; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-		mbar_init(q_full, 1); mbar_init(s_full, 1);
-		for (int t = 0; t < 2; ++t) { mbar_init(&p_full[t], 128); mbar_init(&pv_full[t], 1); }
+		mbar_init(q_full, 1); mbar_init(s_full, 1); mbar_init(p_full, 256); mbar_init(pv_full, 1);
 		fence_barrier_init();
 	}
 	if (warp == W_MMA) tmem_alloc(tmem_slot, 256);
@@ -460,10 +459,10 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 			tma_load_4d(sQ, &tmQ, q_full, 0, q0, h, b);
 			for (int j = 0; j < p.nblk; ++j) {
 				const int s = j % p.stages; const uint32_t ph = (uint32_t)(j / p.stages) & 1;
-				mbar_wait(&k_empty[s], ph ^ 1);
+				mbar_wait_parked(&k_empty[s], ph ^ 1);
 				mbar_expect_tx(&k_full[s], tile_bytes);
 				tma_load_4d(sK + (size_t)s * tile_bytes, &tmK, &k_full[s], 0, j * AK, h, b);
-				mbar_wait(&v_empty[s], ph ^ 1);
+				mbar_wait_parked(&v_empty[s], ph ^ 1);
 				mbar_expect_tx(&v_full[s], tile_bytes);
 				tma_load_4d(sV + (size_t)s * tile_bytes, &tmV, &v_full[s], 0, j * AK, h, b);
 			}
@@ -476,45 +475,57 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 		const uint64_t vdesc0 = make_smem_desc_sw128(smem_u32(sV), CHUNK_BYTES, 1024);
 		const uint32_t tile16 = (uint32_t)tile_bytes >> 4;
 		const int nk16 = p.d16 >> 4;
-		auto issue_qk = [&](int j) {
-			const int s = j % p.stages;
-			mbar_wait(&k_full[s], (uint32_t)(j / p.stages) & 1);
+		// The issuing warp is the critical path between the softmax of block j and that of block j + 1 (PV(j), then QK(j+1)
+		// into the same score columns). Everything that can be waited for early is waited for BEFORE the probabilities
+		// arrive (V(j) and K(j+1) resident); after p_full only one fence and one elected section remain.
+		mbar_wait(q_full, 0);
+		mbar_wait(&k_full[0], 0);
+		tc_fence_after();
+		if (elect_one()) {
+			#pragma unroll
+			for (int kk = 0; kk < 4; ++kk)
+				if (kk < nk16) umma_f16(tmem_base, qdesc0 + (uint64_t)(kk * 2), kdesc0 + (uint64_t)(kk * 2), idesc_qk, kk ? 1u : 0u);
+			umma_commit(s_full);
+			umma_commit(&k_empty[0]);
+			ATTN_TR(2, 0, 3);
+		}
+		__syncwarp();
+		for (int j = 0; j < p.nblk; ++j) {
+			const int s = j % p.stages, s1 = (j + 1) % p.stages;
+			const int valid = min(AK, p.nk - j * AK);
+			const bool more = j + 1 < p.nblk;
+			mbar_wait(&v_full[s], (uint32_t)(j / p.stages) & 1);
+			if (more) mbar_wait(&k_full[s1], (uint32_t)((j + 1) / p.stages) & 1);
+			if (lane == 0) ATTN_TR(3, j, 4);
+			mbar_wait(p_full, (uint32_t)j & 1);
 			tc_fence_after();
 			if (elect_one()) {
-				const uint64_t bd = kdesc0 + (uint64_t)(s * tile16);
+				ATTN_TR(2, j, 1);
+				// V tile: rows = keys (128 B each), 16 keys further = +16 * 128 B; the second half starts 64 keys in.
+				// P in tensor memory: 16 keys = 8 packed 32-bit columns, half b's probabilities start at column 64.
 				#pragma unroll
-				for (int kk = 0; kk < 4; ++kk)
-					if (kk < nk16) umma_f16(tmem_base, qdesc0 + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc_qk, kk ? 1u : 0u);
-				umma_commit(s_full);
-				umma_commit(&k_empty[s]);
-			}
-			__syncwarp();
-		};
-		mbar_wait(q_full, 0);
-		issue_qk(0);
-		for (int j = 0; j < p.nblk; ++j) {
-			const int s = j % p.stages;
-			const int valid = min(AK, p.nk - j * AK);
-			mbar_wait(&v_full[s], (uint32_t)(j / p.stages) & 1);
-			#pragma unroll
-			for (int hf = 0; hf < 2; ++hf) {
-				mbar_wait(&p_full[hf], (uint32_t)j & 1);
-				tc_fence_after();
-				if (elect_one()) {
-					// V tile: rows = keys (128 B each), 16 keys further = +16 * 128 B; the second half starts 64 keys in.
-					// P in tensor memory: 16 keys = 8 packed 32-bit columns, half b's probabilities start at column 64.
+				for (int hf = 0; hf < 2; ++hf) {
 					const uint64_t bd = vdesc0 + (uint64_t)(s * tile16) + (uint64_t)(hf * 512);
 					const uint32_t td = tmem_base + O_BASE + hf * O_STRIDE, ta = tmem_base + hf * 64;
 					const int nkk = (min(64, max(0, valid - hf * 64)) + 15) >> 4;
 					#pragma unroll
 					for (int kk = 0; kk < 4; ++kk)
 						if (kk < nkk) umma_f16_ts(td, ta + kk * 8, bd + (uint64_t)(kk * 128), idesc_pv, (j | kk) ? 1u : 0u);
-					umma_commit(&pv_full[hf]);
-					if (hf == 1) umma_commit(&v_empty[s]);
 				}
-				__syncwarp();
+				umma_commit(pv_full);
+				umma_commit(&v_empty[s]);
+				ATTN_TR(2, j, 2);
+				if (more) {                              // in order after both products: S / P may be overwritten
+					const uint64_t bd = kdesc0 + (uint64_t)(s1 * tile16);
+					#pragma unroll
+					for (int kk = 0; kk < 4; ++kk)
+						if (kk < nk16) umma_f16(tmem_base, qdesc0 + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc_qk, kk ? 1u : 0u);
+					umma_commit(s_full);
+					umma_commit(&k_empty[s1]);
+					ATTN_TR(2, j + 1, 3);
+				}
 			}
-			if (j + 1 < p.nblk) issue_qk(j + 1);        // in order after both products: S / P may be overwritten
+			__syncwarp();
 		}
 	} else {
 		// ===== softmax: warp = quarter (TMEM lanes) + 4 * half (key columns); one (row, half) per thread =====
@@ -526,18 +537,21 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 		const float sl2 = p.scale_log2;
 		float m = -INFINITY, l = 0.f;
 		bool first = true;
+		const bool tr = quarter == 0 && lane == 0;
 
 		auto block = [&](int j, auto full_tag) {
 			constexpr bool FULL = decltype(full_tag)::value;
 			const int valid = FULL ? 64 : min(64, max(0, p.nk - j * AK - hf * 64));      // valid keys of my half
-			mbar_wait(s_full, (uint32_t)j & 1);
+			if (tr) ATTN_TR(hf, j, 0);
+			mbar_wait_parked(s_full, (uint32_t)j & 1);
 			tc_fence_after();
+			if (tr) ATTN_TR(hf, j, 1);
 			uint32_t va[32], vb[32];
 			if (!FULL && valid <= 0) {                                           // nothing of this block belongs to my half
 				#pragma unroll
 				for (int i = 0; i < 16; ++i) va[i] = 0u;
 				tmem_st16(ts, va); tmem_st16(ts + 16, va);
-				tmem_st_wait(); tc_fence_before(); mbar_arrive(&p_full[hf]);
+				tmem_st_wait(); tc_fence_before(); mbar_arrive(p_full);
 				return;
 			}
 			tmem_ld32(ts, va); tmem_ld32(ts + 32, vb);
@@ -563,6 +577,7 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 				}
 			}
 			const float m_blk = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sl2;
+			if (tr) ATTN_TR(hf, j, 2);
 			// Lazy rescaling (as above): keep the old maximum while the block maximum exceeds it by < 2^8.
 			if (first) { m = m_blk; first = false; }
 			else {
@@ -572,7 +587,7 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 					const float corr = ex2_approx(m - m_new);
 					m = m_new;
 					l *= corr;
-					mbar_wait(&pv_full[hf], (uint32_t)(j - 1) & 1);     // my half's PV products so far have landed in O
+					mbar_wait(pv_full, (uint32_t)(j - 1) & 1);     // the PV products so far have landed in O
 					tc_fence_after();
 					#pragma unroll
 					for (int c0 = 0; c0 < 64; c0 += 16) {
@@ -588,6 +603,7 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 				}
 			}
 			const float mneg = -m;
+			if (tr) ATTN_TR(hf, j, 3);
 			float rs4[4] = { 0.f, 0.f, 0.f, 0.f };
 			auto exps = [&](uint32_t* v, int c) {
 				#pragma unroll
@@ -612,9 +628,11 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 			exps(va, 0); exps(vb, 1);
 			finish(va, 0); finish(vb, 1);
 			l += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+			if (tr) ATTN_TR(hf, j, 4);
 			tmem_st_wait();
 			tc_fence_before();
-			mbar_arrive(&p_full[hf]);
+			mbar_arrive(p_full);
+			if (tr) ATTN_TR(hf, j, 5);
 		};
 		const int nfull = p.nk / AK;      // a partial block can only be the last one
 		for (int j = 0; j < nfull; ++j) block(j, std::true_type{});
@@ -622,8 +640,7 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
 		// epilogue: merge the halves. Every thread publishes (m, l) of its (row, half), then takes the 16-column chunks
 		// c with (c & 1) == half of BOTH accumulators of its row.
-		mbar_wait(&pv_full[0], (uint32_t)(p.nblk - 1) & 1);
-		mbar_wait(&pv_full[1], (uint32_t)(p.nblk - 1) & 1);
+		mbar_wait(pv_full, (uint32_t)(p.nblk - 1) & 1);
 		tc_fence_after();
 		exch[hf * 128 + r] = make_float2(m, l);
 		named_bar_sync(1, 256);

@@ -29,20 +29,29 @@ static uint32_t pair_hash(uint32_t k) { k ^= k >> 15; k *= 0x2c1b3c6du; k ^= k >
 int clip_tokenizer_load(const char* dir)
 {
 	if (g_merges) return 1;
-	char path[1024];
+	/* candidates in order: option aux_dir (the reference CLI points it at the directory of its binary,
+	   main_mlimgsynth.c:642-651), $MLIS_B200_DATA, then <directory of this library>/../data */
+	char path[1024], tried[3200]; tried[0] = 0;
 	const char* env = getenv("MLIS_B200_DATA");
-	if (dir && *dir) snprintf(path, sizeof(path), "%s/clip_merges.bin", dir);
-	else if (env && *env) snprintf(path, sizeof(path), "%s/clip_merges.bin", env);
-	else {
-		Dl_info info;
-		if (!dladdr((void*)clip_tokenizer_load, &info) || !info.dli_fname) FAIL(-6, "cannot locate the library directory");
-		snprintf(path, sizeof(path), "%s", info.dli_fname);
-		char* s = strrchr(path, '/');
-		if (s) *s = 0; else strcpy(path, ".");
-		strncat(path, "/../data/clip_merges.bin", sizeof(path) - strlen(path) - 1);
+	FILE* f = NULL;
+	for (int c = 0; c < 3 && !f; ++c) {
+		path[0] = 0;
+		if (c == 0 && dir && *dir) snprintf(path, sizeof(path), "%s/clip_merges.bin", dir);
+		else if (c == 1 && env && *env) snprintf(path, sizeof(path), "%s/clip_merges.bin", env);
+		else if (c == 2) {
+			Dl_info info;
+			if (dladdr((void*)clip_tokenizer_load, &info) && info.dli_fname) {
+				snprintf(path, sizeof(path), "%s", info.dli_fname);
+				char* s = strrchr(path, '/');
+				if (s) *s = 0; else strcpy(path, ".");
+				strncat(path, "/../data/clip_merges.bin", sizeof(path) - strlen(path) - 1);
+			}
+		}
+		if (!path[0]) continue;
+		f = fopen(path, "rb");
+		if (!f) { strncat(tried, path, sizeof(tried) - strlen(tried) - 2); strncat(tried, " ", sizeof(tried) - strlen(tried) - 1); }
 	}
-	FILE* f = fopen(path, "rb");
-	if (!f) FAIL(-6, "CLIP merge table not found: %s (set option aux_dir or MLIS_B200_DATA)", path);
+	if (!f) FAIL(-6, "CLIP merge table not found (tried: %s; set option aux_dir or MLIS_B200_DATA)", tried);
 	g_merges = xmalloc(N_MERGES * 4);
 	size_t got = fread(g_merges, 4, N_MERGES, f);
 	fclose(f);

@@ -35,6 +35,8 @@ struct MLIS_Ctx {
 	float cfg_scale;
 	MLIS_Callback callback; void* callback_user;
 	MLIS_ErrorHandler errh; void* errh_user;
+	int cfg_half; MLIS_B200_CfgExchange cfg_exchange; void* cfg_exchange_user;   /* cross-GPU CFG split (opt-in), -1 = off */
+	float* cfg_other_dev; size_t cfg_other_n;
 	/* runtime */
 	ggml_backend_t backend;
 	TStore tstore; bool tstore_open;
@@ -149,6 +151,7 @@ MLIS_Ctx* mlis_ctx_create_i(int version)
 	S->signature = CTX_SIGNATURE;
 	unet_params_init();            /* sigma tables are needed before the first UNet graph exists (dnsamp_init) */
 	S->cfg_scale = 7;              /* mlimgsynth.c:474 */
+	S->cfg_half = -1;
 	S->n_batch = 1;
 	S->wtype = GGML_TYPE_F16;
 	if (!g_rng_seeded) {
@@ -186,7 +189,7 @@ void mlis_ctx_destroy(MLIS_Ctx** pS)
 	if (S->backend) {
 		graphs_free(S);
 		dnsamp_free(&S->sampler);
-		ggml_b200_free(S->latent_dev); ggml_b200_free(S->image_dev); ggml_b200_free(S->lmask_dev); ggml_b200_free(S->u8_dev);
+		ggml_b200_free(S->latent_dev); ggml_b200_free(S->image_dev); ggml_b200_free(S->lmask_dev); ggml_b200_free(S->u8_dev); ggml_b200_free(S->cfg_other_dev);
 		ggml_backend_free(S->backend);
 	}
 	if (S->tstore_open) tstore_free(&S->tstore);
@@ -807,7 +810,19 @@ static int denoise_dxdt(Solver* sol, float t, const float* x, float* dx)
 	float c_out = 1, c_skip = 0, f = S->cfg_scale;
 	if (S->unet_p->vparam) { c_skip = t / (t * t + 1); c_out = 1 / sqrt(t * t + 1); }   /* reference's mixed float/double forms */
 	float* outs[1] = { dx };
-	if (S->unet.n_rep == 2) {
+	if (S->cfg_half >= 0 && S->cfg_scale > 1) {
+		/* cross-GPU CFG split: this rank evaluated ONE half (its conditioning rows); the peer's half arrives through the
+		   caller's exchange (a 2-rank all-gather of n1 floats per evaluation), then the same combine as below */
+		dev_reserve(&S->cfg_other_dev, &S->cfg_other_n, (size_t)n1);
+		ggml_b200_synchronize();      /* the exchange runs on the caller's stream */
+		int r = S->cfg_exchange(S->cfg_exchange_user, out, S->cfg_other_dev, (size_t)n1);
+		if (r < 0) FAIL(r, "CFG exchange callback failed");
+		const float* oc = S->cfg_half == 0 ? out : S->cfg_other_dev;
+		const float* ou = S->cfg_half == 0 ? S->cfg_other_dev : out;
+		const float* ins[3] = { oc, ou, x };
+		float c[3] = { c_out * f, c_out * (1 - f), c_skip };
+		ggml_b200_lincomb(1, outs, c_skip != 0 ? 3 : 2, ins, c, n1);
+	} else if (S->unet.n_rep == 2) {
 		const float* ins[3] = { out, out + n1, x };
 		float c[3] = { c_out * f, c_out * (1 - f), c_skip };
 		ggml_b200_lincomb(1, outs, c_skip != 0 ? 3 : 2, ins, c, n1);
@@ -910,9 +925,10 @@ static int generate(MLIS_Ctx* S)
 	S->image.flags &= ~HT_READY;
 
 	/* sampler + batched UNet (images x CFG halves) */
-	int n_rep = cfg ? 2 : 1;
+	const bool split = cfg && S->cfg_half >= 0;      /* the other CFG half runs on a peer GPU */
+	int n_rep = (cfg && !split) ? 2 : 1;
 	S->sampler.unet_p = P;
-	S->sampler.nfe_per_dxdt = n_rep;
+	S->sampler.nfe_per_dxdt = cfg ? 2 : 1;
 	S->sampler.c.lmask_dev = lmask_dev; S->sampler.c.mask_pix = (int64_t)w * h;
 	for (int i = 0; i < nb; ++i) { S->rngs[i].seed = g_rng.seed + i; S->rngs[i].offset = g_rng.offset; }
 	S->sampler.rng = S->rngs; S->sampler.n_rng = nb; S->sampler.n_per_image = n_per;
@@ -925,7 +941,8 @@ static int generate(MLIS_Ctx* S)
 		float* cb = xmalloc(nc * nb * n_rep * sizeof(float));
 		float* lb = nl ? xmalloc(nl * nb * n_rep * sizeof(float)) : NULL;
 		for (int r = 0; r < n_rep; ++r) for (int i = 0; i < nb; ++i) {
-			const HTensor *c = r ? &S->ncond : &S->cond, *l = r ? &S->nlabel : &S->label;
+			const bool neg = split ? S->cfg_half == 1 : r == 1;
+			const HTensor *c = neg ? &S->ncond : &S->cond, *l = neg ? &S->nlabel : &S->label;
 			if (ht_count(c) != nc) { free(cb); free(lb); FAIL(-1, "conditioning tensors have different shapes"); }
 			memcpy(cb + nc * (r * nb + i), c->d, nc * sizeof(float));
 			if (lb) memcpy(lb + nl * (r * nb + i), l->d, nl * sizeof(float));
@@ -970,6 +987,14 @@ MLIS_Image* mlis_image_get(MLIS_Ctx* S, int idx)
 	size_t per = (size_t)S->img_w * S->img_h * 3;
 	S->imgex.d = S->imgex_all + per * idx; S->imgex.sz = per; S->imgex.w = S->img_w; S->imgex.h = S->img_h; S->imgex.c = 3; S->imgex.flags = 0;
 	return &S->imgex;
+}
+
+/* Cross-GPU CFG split (opt-in): see include/mlimgsynth_b200.h */
+int mlis_b200_cfg_split_set(MLIS_Ctx* S, int half, MLIS_B200_CfgExchange fn, void* user)
+{
+	if (half >= 0 && (half > 1 || !fn)) { snprintf(S->errstr, sizeof(S->errstr), "cfg split: half must be 0 or 1 and needs an exchange callback"); return MLIS_E_OPT_VALUE; }
+	S->cfg_half = half < 0 ? -1 : half; S->cfg_exchange = fn; S->cfg_exchange_user = user;
+	return 1;
 }
 
 /* The RGB8 images of the last generation / decode as the pack kernel left them in HBM ([n][h][w][3] bytes): multi-GPU callers

@@ -23,9 +23,8 @@ void k_gemm_simt(cudaStream_t s, const View& c, const View& a, const View& b, bo
 // GroupNorm(+affine)(+SiLU): src/dst [W,H,C,N] with channel stride 1 (channels-last).
 // stats: 2*N*groups doubles, zeroed by the caller before launch.
 void k_groupnorm(cudaStream_t s, const View& dst, const View& src, const float* gamma, const float* beta,
-	int groups, float eps, bool silu, double* stats, double* scratch);
-// stats slot: [N][groups][2] doubles + N 32-bit counters (zeroed per run); scratch (shared by all GroupNorm steps of a plan):
-size_t k_groupnorm_scratch_bytes(long long HW, int C, long long N, int groups);
+	int groups, float eps, bool silu, unsigned long long* stats);
+// stats slot: [N][groups][4] 64-bit words (fixed-point sum / sum of squares, integer atomics: order-independent), zeroed per run
 // LayerNorm(+affine) over dim 0 (stride 1), one warp per row.
 void k_layernorm(cudaStream_t s, const View& dst, const View& src, const float* gamma, const float* beta, float eps);
 // GEGLU gate: dst[j,m] = h[j,m] * gelu(h[d+j,m]); h rows have 2d channels.

@@ -436,22 +436,29 @@ void k_gemm_simt(cudaStream_t s, const View& c, const View& a, const View& b, bo
 }
 
 
-// ---- deterministic statistics (no floating-point atomics): every reduction below runs in an order fixed by indices,
-// never by arrival, so a GroupNorm -- and with it a whole graph run -- is bit-reproducible from run to run.
-// Block: per-thread channel sums -> shared memory -> per-channel sums over the block's pixel lanes (double) -> per-group
-// sums over the channels of the slab (double) -> partials[n][block][group]. The LAST block of an image to finish (ticket
-// counter) adds the partials of all blocks in block order and writes stats[n][group] = (sum, sum of squares).
-struct GnRed {
-	double* stats; double* partials; unsigned* counters;
-};
-__device__ __forceinline__ void gn_block_finish(const float* su, const float* sq, bool active, int ch_local, int plane, int planes, int slab, int slab_chunks,
-	int chunks, int cpg, int groups, int n, const GnRed& R, float* smf)
+// ---- deterministic statistics: no floating-point atomics anywhere. Inside a block the per-thread sums are combined in an
+// order fixed by indices (shared memory, per channel over the pixel lanes, then per group over the channels). Across blocks
+// the per-block group sums are added with INTEGER atomics in fixed point: a double d is split into floor(d) and
+// floor((d - floor(d)) * 2^40), both exact 64-bit integers, and integer addition is associative -- the result does not
+// depend on the order in which blocks arrive, so a GroupNorm (and with it a whole graph run) is bit-reproducible.
+// stats layout: [N][groups][4] 64-bit words = (sum hi, sum lo, sum-of-squares hi, sum-of-squares lo), zeroed before the run.
+constexpr double GN_FIX = 1099511627776.0;      // 2^40
+__device__ __forceinline__ void gn_fix_add(unsigned long long* dst, double v)
 {
-	// smf: [planes][slab_chunks * 8][2] floats, then (8-byte aligned) chs[slab_chunks * 8][2] doubles, then parts[4][groups * 2]
-	// doubles: gn_stats_smem() bytes
+	const double hi = floor(v);
+	const long long ihi = (long long)hi, ilo = (long long)((v - hi) * GN_FIX);
+	atomicAdd(dst, (unsigned long long)ihi);        // two's complement: negative sums wrap correctly
+	atomicAdd(dst + 1, (unsigned long long)ilo);
+}
+__device__ __forceinline__ double gn_fix_get(const unsigned long long* src)
+{ return (double)(long long)src[0] + (double)(long long)src[1] * (1.0 / GN_FIX); }
+
+__device__ __forceinline__ void gn_block_finish(const float* su, const float* sq, bool active, int ch_local, int plane, int planes, int slab, int slab_chunks,
+	int chunks, int cpg, int groups, int n, unsigned long long* stats, float* smf)
+{
+	// smf: [planes][slab_chunks * 8][2] floats, then chs[slab_chunks * 8][2] floats: gn_stats_smem() bytes
 	const int nch = slab_chunks * 8;
-	double* chs = reinterpret_cast<double*>(smf + (size_t)planes * nch * 2);
-	__shared__ unsigned s_last;
+	float* chs = smf + (size_t)planes * nch * 2;                 // [nch][2] per-channel sums of this block
 	if (plane < planes) {
 		#pragma unroll
 		for (int j = 0; j < 8; ++j) {
@@ -461,38 +468,20 @@ __device__ __forceinline__ void gn_block_finish(const float* su, const float* sq
 	}
 	__syncthreads();
 	for (int c = threadIdx.x; c < nch; c += blockDim.x) {
-		double a = 0.0, b = 0.0;
-		for (int pl = 0; pl < planes; ++pl) { const float* d = smf + ((size_t)pl * nch + c) * 2; a += (double)d[0]; b += (double)d[1]; }
+		float a = 0.f, b = 0.f;
+		for (int pl = 0; pl < planes; ++pl) { const float* d = smf + ((size_t)pl * nch + c) * 2; a += d[0]; b += d[1]; }
 		chs[c * 2] = a; chs[c * 2 + 1] = b;
 	}
 	__syncthreads();
 	const int c_lo = slab * nch, c_hi = min(chunks * 8, c_lo + nch);        // channels of this slab
-	double* mine = R.partials + ((size_t)n * gridDim.x + blockIdx.x) * groups * 2;
 	for (int g = threadIdx.x; g < groups; g += blockDim.x) {
 		const int g_lo = max(g * cpg, c_lo), g_hi = min((g + 1) * cpg, c_hi);
+		if (g_lo >= g_hi) continue;
 		double a = 0.0, b = 0.0;
-		for (int c = g_lo; c < g_hi; ++c) { a += chs[(c - c_lo) * 2]; b += chs[(c - c_lo) * 2 + 1]; }
-		mine[g * 2] = a; mine[g * 2 + 1] = b;
+		for (int c = g_lo; c < g_hi; ++c) { a += (double)chs[(c - c_lo) * 2]; b += (double)chs[(c - c_lo) * 2 + 1]; }
+		unsigned long long* dst = stats + ((size_t)n * groups + g) * 4;
+		gn_fix_add(dst, a); gn_fix_add(dst + 2, b);
 	}
-	__threadfence();
-	__syncthreads();
-	if (threadIdx.x == 0) s_last = (atomicAdd(&R.counters[n], 1u) == gridDim.x - 1) ? 1u : 0u;
-	__syncthreads();
-	if (!s_last) return;
-	__threadfence();
-	const double* all = R.partials + (size_t)n * gridDim.x * groups * 2;
-	double* parts = chs + (size_t)nch * 2;                       // [4][groups * 2]
-	const int npair = groups * 2;
-	for (int i = threadIdx.x; i < npair * 4; i += blockDim.x) {   // (part, pair): blocks part, part + 4, ... in order
-		const int part = i / npair, pair = i - part * npair;
-		double a = 0.0;
-		for (unsigned bb = part; bb < gridDim.x; bb += 4) a += all[(size_t)bb * npair + pair];
-		parts[i] = a;
-	}
-	__syncthreads();
-	for (int pair = threadIdx.x; pair < npair; pair += blockDim.x)
-		R.stats[(size_t)n * npair + pair] = ((parts[pair] + parts[npair + pair]) + parts[2 * npair + pair]) + parts[3 * npair + pair];
-	if (threadIdx.x == 0) R.counters[n] = 0;                    // ready for the next run even without the memset
 }
 
 // ------------------------------------------------------------------ GroupNorm (+affine, +SiLU), channels-last f16
@@ -506,7 +495,7 @@ __device__ __forceinline__ void gn_block_finish(const float* su, const float* sq
 // double-precision statistics in global memory.
 template <typename T>
 __global__ void gn_stats_kernel(const T* __restrict__ x, long long HW, int C, int cpg, int groups,
-	long long img_stride, long long pix_stride, GnRed R, int pix_per_block, int slab_chunks, int nslabs)
+	long long img_stride, long long pix_stride, unsigned long long* __restrict__ stats, int pix_per_block, int slab_chunks, int nslabs)
 {
 	extern __shared__ __align__(16) float sm[];
 	const int n = blockIdx.y;
@@ -537,20 +526,20 @@ __global__ void gn_stats_kernel(const T* __restrict__ x, long long HW, int C, in
 			for (int j = 0; j < 8; ++j) { su[j] += v[j]; sq[j] += v[j] * v[j]; }
 		}
 	}
-	gn_block_finish(su, sq, active, (int)(threadIdx.x % slab_chunks), plane, planes, slab, slab_chunks, chunks, cpg, groups, n, R, sm);
+	gn_block_finish(su, sq, active, (int)(threadIdx.x % slab_chunks), plane, planes, slab, slab_chunks, chunks, cpg, groups, n, stats, sm);
 }
 
 template <typename TI, typename TO>
 __global__ void gn_apply_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long HW, int C, int cpg, int groups,
 	long long img_stride, long long pix_stride, long long oimg_stride, long long opix_stride,
-	const float* __restrict__ gamma, const float* __restrict__ beta, const double* __restrict__ stats,
+	const float* __restrict__ gamma, const float* __restrict__ beta, const unsigned long long* __restrict__ stats,
 	float eps, int silu)
 {
 	extern __shared__ float sm[];  // mean[groups], rstd[groups]
 	int n = blockIdx.y;
 	double cnt = (double)HW * cpg;
 	for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-		double su = stats[((long long)n * groups + g) * 2], sq = stats[((long long)n * groups + g) * 2 + 1];
+		double su = gn_fix_get(stats + ((long long)n * groups + g) * 4), sq = gn_fix_get(stats + ((long long)n * groups + g) * 4 + 2);
 		double mean = su / cnt, var = sq / cnt - mean * mean;
 		if (var < 0) var = 0;
 		sm[g] = (float)mean;
@@ -614,7 +603,7 @@ constexpr int GN_BLOCKS_PER_SM = 5;      // both fast kernels are compiled for 5
 
 __global__ void __launch_bounds__(256, GN_BLOCKS_PER_SM)
 gn_stats_fast_kernel(const __half* __restrict__ x, long long HW, int C, int cpg, int groups,
-	long long img_stride, long long pix_stride, GnRed R, int pix_per_block, int slab_chunks, int nslabs)
+	long long img_stride, long long pix_stride, unsigned long long* __restrict__ stats, int pix_per_block, int slab_chunks, int nslabs)
 {
 	extern __shared__ __align__(16) float sm[];
 	const int n = blockIdx.y;
@@ -645,7 +634,7 @@ gn_stats_fast_kernel(const __half* __restrict__ x, long long HW, int C, int cpg,
 			for (int j = 0; j < 8; ++j) { su[j] += v[j]; sq[j] = fmaf(v[j], v[j], sq[j]); }
 		}
 	}
-	gn_block_finish(su, sq, active, (int)(threadIdx.x % slab_chunks), plane, planes, slab, slab_chunks, chunks, cpg, groups, n, R, sm);
+	gn_block_finish(su, sq, active, (int)(threadIdx.x % slab_chunks), plane, planes, slab, slab_chunks, chunks, cpg, groups, n, stats, sm);
 }
 
 // x * sigmoid(x) = x * (0.5 + 0.5 tanh(x / 2)): one MUFU op per element (tanh.approx) instead of ex2 + rcp
@@ -660,7 +649,7 @@ template <bool SILU>
 __global__ void __launch_bounds__(256, GN_BLOCKS_PER_SM)
 gn_apply_fast_kernel(const __half* __restrict__ x, __half* __restrict__ y, long long HW, int C, int cpg, int groups,
 	long long img_stride, long long pix_stride, long long oimg_stride, long long opix_stride,
-	const float* __restrict__ gamma, const float* __restrict__ beta, const double* __restrict__ stats,
+	const float* __restrict__ gamma, const float* __restrict__ beta, const unsigned long long* __restrict__ stats,
 	float eps, int pix_per_block, int slab_chunks, int nslabs)
 {
 	extern __shared__ float sm[];  // mean[groups], rstd[groups]: the double-precision finish runs once per group and block
@@ -668,7 +657,7 @@ gn_apply_fast_kernel(const __half* __restrict__ x, __half* __restrict__ y, long 
 	const int tile = blockIdx.x / nslabs, slab = blockIdx.x - tile * nslabs;
 	const double cnt = (double)HW * cpg;
 	for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-		const double su = stats[((long long)n * groups + g) * 2], sq = stats[((long long)n * groups + g) * 2 + 1];
+		const double su = gn_fix_get(stats + ((long long)n * groups + g) * 4), sq = gn_fix_get(stats + ((long long)n * groups + g) * 4 + 2);
 		const double mean = su / cnt; double var = sq / cnt - mean * mean; if (var < 0) var = 0;
 		sm[g] = (float)mean;
 		sm[groups + g] = (float)(1.0 / sqrt(var + (double)eps));
@@ -780,7 +769,7 @@ static void gn_small_launch(cudaStream_t s, bool silu, dim3 grid, const __half* 
 }
 
 static size_t gn_stats_smem(int planes, int slab_chunks, int groups)
-{ return (size_t)planes * slab_chunks * 8 * 2 * sizeof(float) + (size_t)slab_chunks * 8 * 2 * sizeof(double) + (size_t)4 * groups * 2 * sizeof(double); }
+{ (void)groups; return (size_t)planes * slab_chunks * 8 * 2 * sizeof(float) + (size_t)slab_chunks * 8 * 2 * sizeof(float); }
 
 // launch geometry of the statistics pass (shared with the planner's scratch sizing)
 struct GnGeom { int threads, planes, slab_chunks, nslabs, pix_per_block; unsigned grid_x; };
@@ -809,15 +798,9 @@ static GnGeom gn_geom(long long HW, int C, long long N, bool fast)
 	return g;
 }
 
-size_t k_groupnorm_scratch_bytes(long long HW, int C, long long N, int groups)
-{
-	const unsigned gx = std::max(gn_geom(HW, C, N, true).grid_x, gn_geom(HW, C, N, false).grid_x);
-	return (size_t)N * gx * groups * 2 * sizeof(double);
-}
-
-// stats: [N][groups][2] doubles followed by N 32-bit block counters (zeroed before the run); scratch: k_groupnorm_scratch_bytes
+// stats: [N][groups][4] 64-bit words (fixed-point sums, see gn_fix_add), zeroed before the run
 void k_groupnorm(cudaStream_t s, const View& dst, const View& src, const float* gamma, const float* beta,
-	int groups, float eps, bool silu, double* stats, double* scratch)
+	int groups, float eps, bool silu, unsigned long long* stats)
 {
 	int C = (int)src.ne[2]; long long W = src.ne[0], H = src.ne[1], N = src.ne[3], HW = W * H;
 	int cpg = (C + groups - 1) / groups;
@@ -843,10 +826,9 @@ void k_groupnorm(cudaStream_t s, const View& dst, const View& src, const float* 
 		const int slab_chunks = G.slab_chunks, nslabs = G.nslabs, threads = G.threads, pix_per_block = G.pix_per_block;
 		dim3 grid(G.grid_x, (unsigned)N);
 		const size_t smem = groups * 2 * sizeof(float);
-		const GnRed R = { stats, scratch, reinterpret_cast<unsigned*>(stats + (size_t)N * groups * 2) };
 		static bool attr = false;
 		if (!attr) { CUDA_CHECK(cudaFuncSetAttribute(gn_stats_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
-		gn_stats_fast_kernel<<<grid, threads, gn_stats_smem(G.planes, slab_chunks, groups), s>>>((const __half*)src.ptr, HW, C, cpg, groups, src.st[3], src.st[0], R, pix_per_block, slab_chunks, nslabs);
+		gn_stats_fast_kernel<<<grid, threads, gn_stats_smem(G.planes, slab_chunks, groups), s>>>((const __half*)src.ptr, HW, C, cpg, groups, src.st[3], src.st[0], stats, pix_per_block, slab_chunks, nslabs);
 		if (silu)
 			gn_apply_fast_kernel<true><<<grid, threads, smem, s>>>((const __half*)src.ptr, (__half*)dst.ptr, HW, C, cpg, groups, src.st[3], src.st[0],
 				dst.st[3], dst.st[0], gamma, beta, stats, eps, pix_per_block, slab_chunks, nslabs);
@@ -860,12 +842,11 @@ void k_groupnorm(cudaStream_t s, const View& dst, const View& src, const float* 
 	const int threads = G.threads, slab_chunks = G.slab_chunks, nslabs = G.nslabs, pix_per_block = G.pix_per_block;
 	dim3 g1(G.grid_x, (unsigned)N);
 	size_t smem = groups * 2 * sizeof(float);
-	const GnRed R = { stats, scratch, reinterpret_cast<unsigned*>(stats + (size_t)N * groups * 2) };
 	const size_t smem1 = gn_stats_smem(G.planes, slab_chunks, groups);
 	if (src.dt == DT_F16)
-		gn_stats_kernel<__half><<<g1, threads, smem1, s>>>((const __half*)src.ptr, HW, C, cpg, groups, src.st[3], src.st[0], R, pix_per_block, slab_chunks, nslabs);
+		gn_stats_kernel<__half><<<g1, threads, smem1, s>>>((const __half*)src.ptr, HW, C, cpg, groups, src.st[3], src.st[0], stats, pix_per_block, slab_chunks, nslabs);
 	else
-		gn_stats_kernel<float><<<g1, threads, smem1, s>>>((const float*)src.ptr, HW, C, cpg, groups, src.st[3], src.st[0], R, pix_per_block, slab_chunks, nslabs);
+		gn_stats_kernel<float><<<g1, threads, smem1, s>>>((const float*)src.ptr, HW, C, cpg, groups, src.st[3], src.st[0], stats, pix_per_block, slab_chunks, nslabs);
 	long long total = HW * (C / 8);
 	dim3 g2((unsigned)std::min<long long>((total + threads - 1) / threads, 148 * 8), (unsigned)N);
 	if (src.dt == DT_F16 && dst.dt == DT_F16)

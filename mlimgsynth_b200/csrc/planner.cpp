@@ -71,8 +71,7 @@ struct Plan {
 	void* persist = nullptr; size_t persist_bytes = 0;
 	size_t zero_off = 0, zero_bytes = 0;   // region of the arena cleared at the start of each run
 	int zero_buf = -1;
-	size_t gn_scratch_bytes = 0;           // per-block partial sums of the (deterministic) GroupNorm statistics, shared by all steps
-	int gn_scratch_buf = -1;
+
 	cudaGraphExec_t exec = nullptr;
 	bool use_graph = true;
 	uint64_t launches_per_run = 0;
@@ -896,8 +895,7 @@ void Builder::plan_node(ggml_tensor* t)
 		if (has_w) { s.bias = gw; s.has_bias = true; }
 		if (has_b) { s.rowvec = gb; s.has_rowvec = true; }
 		s.stats_off = P->zero_bytes;
-		P->zero_bytes += (size_t)2 * groups * t->ne[3] * sizeof(double) + ((size_t)t->ne[3] * sizeof(unsigned) + 7) / 8 * 8;   // sums + per-image block counters
-		P->gn_scratch_bytes = std::max(P->gn_scratch_bytes, k_groupnorm_scratch_bytes(t->ne[0] * t->ne[1], (int)t->ne[2], t->ne[3], groups));
+		P->zero_bytes += (size_t)4 * groups * t->ne[3] * sizeof(unsigned long long);     // fixed-point (hi, lo) sum and sum of squares
 		done[t] = true;
 		finish(last, o);
 	} break;
@@ -1061,10 +1059,7 @@ static void assign_memory(Plan* P)
 		P->bufs.push_back(Buf{BUF_ARENA, (P->zero_bytes + 255) / 256 * 256, nullptr, 0, n, 0});
 		P->zero_buf = (int)P->bufs.size() - 1;
 	}
-	if (P->gn_scratch_bytes) {
-		P->bufs.push_back(Buf{BUF_ARENA, (P->gn_scratch_bytes + 255) / 256 * 256, nullptr, 0, n, 0});
-		P->gn_scratch_buf = (int)P->bufs.size() - 1;
-	}
+
 	// persistent buffers
 	size_t poff = 0;
 	for (Buf& b : P->bufs) if (b.kind == BUF_PERSIST) { b.off = poff; poff += b.bytes; }
@@ -1129,8 +1124,7 @@ static void run_step(Plan* P, Step& s, cudaStream_t st)
 		k_groupnorm(st, view_of(P, s.out), view_of(P, s.in[0]),
 			s.has_bias ? (const float*)buf_ptr(P, s.bias) : nullptr, s.has_rowvec ? (const float*)buf_ptr(P, s.rowvec) : nullptr,
 			s.iparam[0], s.fparam, s.iparam[1] != 0,
-			(double*)((char*)P->arena + P->bufs[P->zero_buf].off + s.stats_off),
-			(double*)((char*)P->arena + P->bufs[P->gn_scratch_buf].off));
+			(unsigned long long*)((char*)P->arena + P->bufs[P->zero_buf].off + s.stats_off));
 		break;
 	case S_LAYERNORM:
 		k_layernorm(st, view_of(P, s.out), view_of(P, s.in[0]),

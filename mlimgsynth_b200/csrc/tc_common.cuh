@@ -34,6 +34,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 		}
 	}
 }
+// Wait that parks the thread in hardware (suspend-time hint) instead of polling: for warps that wait a long time next to a
+// warp on the critical path (the MMA issuer shares its SM sub-partition's issue port with them).
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity)
+{
+	uint32_t ok = 0;
+	long long t0 = 0;
+	while (true) {
+		asm volatile("{\n\t.reg .pred p;\n\t"
+			"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+			"selp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(200000u) : "memory");
+		if (ok) return;
+		if (!t0) t0 = clock64();
+		else if (clock64() - t0 > 4000000000LL) {
+			printf("[ggml_b200] tcgen05 kernel: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+			__trap();
+		}
+	}
+}
 // One lane of a converged warp (warp-uniform control flow around it keeps descriptors in uniform registers).
 __device__ __forceinline__ bool elect_one()
 {

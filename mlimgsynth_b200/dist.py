@@ -90,6 +90,43 @@ def vae_decode_tiled(ctx, latent, rank=None, world=None, dst=0):
     return ctx.image(0)
 
 
+def cfg_split_enable(ctx, group=None):
+    """Opt-in cross-GPU CFG split for fewer images than GPUs: the two ranks of `group` (default: the world,
+    which must then have exactly two ranks) run the SAME generation -- same options, seed, prompts -- and each evaluates one
+    CFG half per UNet evaluation; the halves are exchanged with one 2-rank NCCL all-gather of the UNet output
+    (64-256 KB per image). Both ranks end with the same latent / image. Call ctx.cfg_split(None) to switch it off."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if world != 2:
+        raise ValueError("the CFG split pairs exactly two ranks")
+    half = dist.get_rank(group)
+    bufs = {}
+
+    def exchange(mine_ptr, other_ptr, n):
+        if n not in bufs:
+            bufs[n] = torch.empty((2, n), dtype=torch.float32, device="cuda")
+        mine = torch.as_tensor(_DeviceWords(mine_ptr, n), device="cuda")
+        other = torch.as_tensor(_DeviceWords(other_ptr, n), device="cuda")
+        if dist.get_backend(group) == "nccl":
+            dist.all_gather_into_tensor(bufs[n], mine, group=group)
+            other.copy_(bufs[n][1 - half])
+        else:                           # host-staged (gloo): used by the single-GPU test, two processes on one device
+            parts = [torch.empty(n, dtype=torch.float32) for _ in range(2)]
+            dist.all_gather(parts, mine.cpu(), group=group)
+            other.copy_(parts[1 - half])
+        torch.cuda.current_stream().synchronize()
+    ctx.cfg_split(half, exchange)
+    return half
+
+
+class _DeviceWords:
+    """Zero-copy f32 view of foreign device memory for torch (CUDA array interface)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
 class _DeviceBytes:
     """Zero-copy view of foreign device memory for torch (CUDA array interface)."""
 

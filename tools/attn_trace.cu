@@ -60,7 +60,8 @@ int main(int argc, char** argv)
 			printf("\n");
 		}
 	}
-	for (int j = 1; j < 3; ++j) { printf("blk %d tile 0 per-MMA issue stamps (PV):", j); for (int e = 0; e < 8; ++e) printf(" %7lld", T(3, j, e)); printf("\n"); }
+	printf("mma warp detail: 0 before k_full wait  1 after  2 elected (QK issue starts)  3 before v_full wait  4 after  5 p_full[a] seen  6 p_full[b] seen\n");
+	for (int j = 1; j < nshow; ++j) { printf("blk %2d mma detail:", j); for (int e = 0; e < 8; ++e) printf(" %7lld", T(3, j, e)); printf("\n"); }
 	// check a few outputs against a straightforward CPU evaluation (row 0 and row nq-1 of head 0, image 0)
 	std::vector<__half> ho(nQ);
 	CUDA_CHECK(cudaMemcpy(ho.data(), o, nQ * 2, cudaMemcpyDeviceToHost));
