@@ -690,6 +690,275 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 }
 
 
+
+// ------------------------------------------------------------------ heads up to 64 wide: quarter-split form, double-buffered scores
+// The key-split kernel above still serialises, per CTA, softmax(j) -> PV(j) -> QK(j+1) -> softmax(j+1): its eight softmax warps wait
+// ~950 clk per key block for the issuing warp and the tensor pipe (timeline in profiles/r2_attention_microbench.md). Here ONE CTA per
+// SM owns all 512 tensor-memory columns:
+//   S0 | S1   two score buffers: QK(j+2) is issued as soon as PV(j) has been issued, i.e. the scores of the next TWO blocks
+//             are normally complete before the softmax warps ask for them -- the products leave the critical path;
+//   O_0..O_3  one output accumulator per key quarter.
+// SIXTEEN softmax warps: warp = lane group (TMEM lanes) + 4 * key quarter; a thread owns 32 scores of one row per block (one
+// tcgen05.ld), its own running maximum / sum, and writes 16 packed probability columns over the start of its own scores. The
+// warps of a sub-partition only meet at the MUFU pipe: four of them per sub-partition keep it fed while others load, pack or wait.
+// Epilogue: the four partial (m, l, O) of a row are merged through 4 KB of shared memory.
+template <int N_POLY>
+__global__ void __launch_bounds__(576, 1)
+attn_split4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+	const AttnParams p)
+{
+	extern __shared__ __align__(1024) uint8_t smem_raw[];
+	uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+	const int tile_bytes = p.dchunks * CHUNK_BYTES;       // dchunks == 1 here (d <= 64)
+	uint8_t* sQ = smem;
+	uint8_t* sK = sQ + tile_bytes;
+	uint8_t* sV = sK + (size_t)p.stages * tile_bytes;
+	uint64_t* bars = (uint64_t*)(sV + (size_t)p.stages * tile_bytes);
+	uint64_t* q_full = bars;                        // [1]
+	uint64_t* k_full = q_full + 1;                  // [stages]
+	uint64_t* k_empty = k_full + A_MAX_STAGES;
+	uint64_t* v_full = k_empty + A_MAX_STAGES;
+	uint64_t* v_empty = v_full + A_MAX_STAGES;
+	uint64_t* s_full = v_empty + A_MAX_STAGES;      // [2]   QK into score buffer b done
+	uint64_t* p_full = s_full + 2;                  // [2]   probabilities of buffer b written (512 arrivals)
+	uint64_t* pv_full = p_full + 2;                 // [1]   PV products of a block done
+	uint32_t* tmem_slot = (uint32_t*)(pv_full + 1);
+	float2* exch = (float2*)(tmem_slot + 2);        // [4 quarters][128 rows] (running maximum, running sum)
+
+	const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
+	const int q0 = blockIdx.x * AQ, h = blockIdx.y, b = blockIdx.z;
+	constexpr uint32_t O_BASE = 256, O_STRIDE = 64;
+	constexpr int W_TMA = 16, W_MMA = 17;
+
+	if (threadIdx.x == 0) {
+		tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+		for (int s = 0; s < p.stages; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+		mbar_init(q_full, 1); mbar_init(pv_full, 1);
+		for (int t = 0; t < 2; ++t) { mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 512); }
+		fence_barrier_init();
+	}
+	if (warp == W_MMA) tmem_alloc(tmem_slot, 512);
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = uniform_u32(*tmem_slot);
+
+	if (warp == W_TMA) {
+		if (lane == 0) {
+			mbar_expect_tx(q_full, tile_bytes);
+			tma_load_4d(sQ, &tmQ, q_full, 0, q0, h, b);
+			// K runs two blocks ahead of V (QK(j+2) is issued together with PV(j)): issue order K0 K1 [V0 K2] [V1 K3] ...
+			auto load_k = [&](int j) {
+				const int s = j % p.stages; const uint32_t ph = (uint32_t)(j / p.stages) & 1;
+				mbar_wait_parked(&k_empty[s], ph ^ 1);
+				mbar_expect_tx(&k_full[s], tile_bytes);
+				tma_load_4d(sK + (size_t)s * tile_bytes, &tmK, &k_full[s], 0, j * AK, h, b);
+			};
+			auto load_v = [&](int j) {
+				const int s = j % p.stages; const uint32_t ph = (uint32_t)(j / p.stages) & 1;
+				mbar_wait_parked(&v_empty[s], ph ^ 1);
+				mbar_expect_tx(&v_full[s], tile_bytes);
+				tma_load_4d(sV + (size_t)s * tile_bytes, &tmV, &v_full[s], 0, j * AK, h, b);
+			};
+			load_k(0);
+			if (p.nblk > 1) load_k(1);
+			for (int j = 0; j < p.nblk; ++j) { load_v(j); if (j + 2 < p.nblk) load_k(j + 2); }
+		}
+	} else if (warp == W_MMA) {
+		const uint32_t idesc_qk = make_idesc_f16(AQ, AK, 0, 0);
+		const uint32_t idesc_pv = make_idesc_f16(AQ, p.d16, 0, 1);     // A = P (TMEM), B = V MN-major ([key][d], d contiguous)
+		const uint64_t qdesc0 = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+		const uint64_t kdesc0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+		const uint64_t vdesc0 = make_smem_desc_sw128(smem_u32(sV), CHUNK_BYTES, 1024);
+		const uint32_t tile16 = (uint32_t)tile_bytes >> 4;
+		const int nk16 = p.d16 >> 4;
+		auto qk_mmas = [&](int j) {          // called by the elected lane: S[j & 1] = Q K(j)^T
+			const int s = j % p.stages;
+			const uint64_t bd = kdesc0 + (uint64_t)(s * tile16);
+			const uint32_t td = tmem_base + (uint32_t)(j & 1) * 128;
+			#pragma unroll
+			for (int kk = 0; kk < 4; ++kk)
+				if (kk < nk16) umma_f16(td, qdesc0 + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc_qk, kk ? 1u : 0u);
+			umma_commit(&s_full[j & 1]);
+			umma_commit(&k_empty[s]);
+		};
+		mbar_wait(q_full, 0);
+		mbar_wait(&k_full[0], 0);
+		if (p.nblk > 1) mbar_wait(&k_full[1 % p.stages], (uint32_t)(1 / p.stages) & 1);
+		tc_fence_after();
+		if (elect_one()) { qk_mmas(0); if (p.nblk > 1) qk_mmas(1); }
+		__syncwarp();
+		for (int j = 0; j < p.nblk; ++j) {
+			const int s = j % p.stages;
+			const int valid = min(AK, p.nk - j * AK);
+			const bool more = j + 2 < p.nblk;
+			mbar_wait(&v_full[s], (uint32_t)(j / p.stages) & 1);
+			if (more) mbar_wait(&k_full[(j + 2) % p.stages], (uint32_t)((j + 2) / p.stages) & 1);
+			mbar_wait(&p_full[j & 1], (uint32_t)(j >> 1) & 1);
+			tc_fence_after();
+			if (elect_one()) {
+				// V tile: rows = keys (128 B each), 16 keys further = +16 * 128 B; quarter q starts 32 keys * q in.
+				// P in tensor memory: 16 keys = 8 packed 32-bit columns, quarter q's probabilities start at column 32 q of S[j & 1].
+				#pragma unroll
+				for (int q = 0; q < 4; ++q) {
+					const uint64_t bd = vdesc0 + (uint64_t)(s * tile16) + (uint64_t)(q * 256);
+					const uint32_t td = tmem_base + O_BASE + q * O_STRIDE, ta = tmem_base + (uint32_t)(j & 1) * 128 + q * 32;
+					const int nkk = (min(32, max(0, valid - q * 32)) + 15) >> 4;
+					#pragma unroll
+					for (int kk = 0; kk < 2; ++kk)
+						if (kk < nkk) umma_f16_ts(td, ta + kk * 8, bd + (uint64_t)(kk * 128), idesc_pv, (j | kk) ? 1u : 0u);
+				}
+				umma_commit(pv_full);
+				umma_commit(&v_empty[s]);
+				if (more) qk_mmas(j + 2);                // in order after the products: S[j & 1] / P may be overwritten
+			}
+			__syncwarp();
+		}
+	} else {
+		// ===== softmax: warp = lane group (TMEM lanes) + 4 * key quarter; one (row, quarter) per thread =====
+		const int kq = warp >> 2, lg = warp & 3;
+		const int r = lg * 32 + lane;
+		const uint32_t lane_off = (uint32_t)(lg * 32) << 16;
+		const uint32_t ts0 = tmem_base + lane_off + kq * 32;                     // my 32 scores in buffer 0 (+128 for buffer 1)
+		const uint32_t to = tmem_base + O_BASE + kq * O_STRIDE + lane_off;       // my quarter's output accumulator of this row
+		const float sl2 = p.scale_log2;
+		float m = -INFINITY, l = 0.f;
+		bool first = true;
+
+		auto block = [&](int j, auto full_tag) {
+			constexpr bool FULL = decltype(full_tag)::value;
+			const int valid = FULL ? 32 : min(32, max(0, p.nk - j * AK - kq * 32));      // valid keys of my quarter
+			const uint32_t ts = ts0 + (uint32_t)(j & 1) * 128;
+			mbar_wait_parked(&s_full[j & 1], (uint32_t)(j >> 1) & 1);
+			tc_fence_after();
+			uint32_t v[32];
+			if (!FULL && valid <= 0) {                                           // nothing of this block belongs to my quarter
+				#pragma unroll
+				for (int i = 0; i < 16; ++i) v[i] = 0u;
+				tmem_st16(ts, v);
+				tmem_st_wait(); tc_fence_before(); mbar_arrive(&p_full[j & 1]);
+				return;
+			}
+			tmem_ld32(ts, v);
+			tmem_ld_wait();
+			float mx4[4] = { -INFINITY, -INFINITY, -INFINITY, -INFINITY };
+			if (FULL) {
+				#pragma unroll
+				for (int i = 0; i < 32; i += 8) {
+					mx4[0] = max3f(mx4[0], __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+					mx4[1] = max3f(mx4[1], __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+					mx4[2] = max3f(mx4[2], __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+					mx4[3] = max3f(mx4[3], __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
+				}
+			} else {
+				#pragma unroll
+				for (int i = 0; i < 32; ++i) if (i < valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
+			}
+			const float m_blk = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sl2;
+			// Lazy rescaling (as above): keep the old maximum while the block maximum exceeds it by < 2^8.
+			if (first) { m = m_blk; first = false; }
+			else {
+				const bool need = m_blk > m + 8.0f;
+				if (__any_sync(0xffffffffu, need)) {
+					const float m_new = need ? m_blk : m;
+					const float corr = ex2_approx(m - m_new);
+					m = m_new;
+					l *= corr;
+					// PV(j-2) completed before QK(j) did (in-order tensor pipe), so the barrier's open phase is j-1 or later:
+					// this waits exactly for PV(j-1), after which no product is in flight towards my accumulator
+					mbar_wait(pv_full, (uint32_t)(j - 1) & 1);
+					tc_fence_after();
+					#pragma unroll
+					for (int c0 = 0; c0 < 64; c0 += 16) {
+						if (c0 < p.d16) {
+							uint32_t o[16];
+							tmem_ld16(to + c0, o);
+							tmem_ld_wait();
+							#pragma unroll
+							for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+							tmem_st16(to + c0, o);
+						}
+					}
+				}
+			}
+			const float mneg = -m;
+			float rs4[4] = { 0.f, 0.f, 0.f, 0.f };
+			uint32_t packed[16];
+			#pragma unroll
+			for (int i = 0; i < 32; i += 2) {
+				float e0, e1;
+				{ const float xs = fmaf(__uint_as_float(v[i]), sl2, mneg); e0 = (i & 7) < N_POLY ? ex2_poly(xs) : ex2_approx(xs); }
+				{ const float xs = fmaf(__uint_as_float(v[i + 1]), sl2, mneg); e1 = ((i + 1) & 7) < N_POLY ? ex2_poly(xs) : ex2_approx(xs); }
+				if (!FULL) { if (i >= valid) e0 = 0.f; if (i + 1 >= valid) e1 = 0.f; }
+				rs4[(i >> 1) & 3] += e0 + e1;
+				__half2 hh = __floats2half2_rn(e0, e1);
+				packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+			}
+			tmem_st16(ts, packed);
+			l += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+			tmem_st_wait();
+			tc_fence_before();
+			mbar_arrive(&p_full[j & 1]);
+		};
+		const int nfull = p.nk / AK;      // a partial block can only be the last one
+		for (int j = 0; j < nfull; ++j) block(j, std::true_type{});
+		if (nfull < p.nblk) block(nfull, std::false_type{});
+
+		// epilogue: merge the quarters. Every thread publishes (m, l) of its (row, quarter); quarter c takes the 16-column chunk c
+		// of all four accumulators of its row.
+		mbar_wait(pv_full, (uint32_t)(p.nblk - 1) & 1);
+		tc_fence_after();
+		exch[kq * 128 + r] = make_float2(first ? -INFINITY : m, l);
+		named_bar_sync(1, 512);
+		float mq[4], lq[4], M = -INFINITY;
+		#pragma unroll
+		for (int q = 0; q < 4; ++q) { const float2 e = exch[q * 128 + r]; mq[q] = e.x; lq[q] = e.y; M = fmaxf(M, e.x); }
+		float wq[4], L = 0.f;
+		#pragma unroll
+		for (int q = 0; q < 4; ++q) { wq[q] = (mq[q] == -INFINITY) ? 0.f : ex2_approx(mq[q] - M); L += lq[q] * wq[q]; }
+		const float inv = L > 0.f ? 1.0f / L : 0.f;
+		const int c0 = kq * 16;
+		if (c0 < p.d16) {
+			const long long tok = (long long)q0 + r;
+			float o[16];
+			#pragma unroll
+			for (int i = 0; i < 16; ++i) o[i] = 0.f;
+			#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				uint32_t oq[16];
+				tmem_ld16(tmem_base + O_BASE + q * O_STRIDE + lane_off + c0, oq);
+				tmem_ld_wait();
+				const float w = wq[q] * inv;
+				#pragma unroll
+				for (int i = 0; i < 16; ++i) o[i] = fmaf(__uint_as_float(oq[i]), w, o[i]);
+			}
+			if (tok < p.nq) {
+				__half* op = (__half*)p.o + tok * p.so_t + (long long)h * p.so_h + (long long)b * p.so_b;
+				const bool vec = ((((uintptr_t)op) & 15) == 0);
+				#pragma unroll
+				for (int h8 = 0; h8 < 16; h8 += 8) {
+					const int cc = c0 + h8;
+					if (cc < p.d) {
+						if (vec && cc + 8 <= p.d) {
+							uint4 o4; __half2* hp = reinterpret_cast<__half2*>(&o4);
+							#pragma unroll
+							for (int i = 0; i < 4; ++i) hp[i] = __floats2half2_rn(o[h8 + 2 * i], o[h8 + 2 * i + 1]);
+							*reinterpret_cast<uint4*>(op + cc) = o4;
+						} else {
+							#pragma unroll
+							for (int i = 0; i < 8; ++i) if (cc + i < p.d) op[cc + i] = __float2half_rn(o[h8 + i]);
+						}
+					}
+				}
+			}
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == W_MMA) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+
 // ------------------------------------------------------------------ single key block (cross-attention, nk <= 128)
 // The text context of a cross-attention has 77 keys (unet.c:110-145): one key block. With one (pair of) query tile(s)
 // per CTA such a launch is a chain of latencies -- load, QK^T, softmax, PV, store -- that nothing overlaps, ~6 us per
@@ -943,12 +1212,15 @@ AttnTC* attn_tc_prepare(const View& o, const View& q, const View& k, const View&
 	// heads up to 64 wide: one tile per CTA, two CTAs per SM (measured 7-12 % faster than two ping-pong tiles in one CTA)
 	{ const char* e = getenv("GGML_B200_ATTN_DUAL"); p.dual = (e ? atoi(e) : 1) && p.d16 <= 64 && p.nblk > 1; }
 	// key-split form of the dual layout (eight softmax warps per CTA): default for heads up to 64 wide
-	{ const char* e = getenv("GGML_B200_ATTN_SPLIT"); p.split = p.dual && (e ? atoi(e) : 1); }
+	// GGML_B200_ATTN_SPLIT: 0 = one row per thread (round-1 dual form), 2 = key halves, two CTAs per SM (default: 837 / 272 / 340 us on
+	// the three shapes of profiles/r2_attention_microbench.md against 841 / 300 / 392 us), 4 = key quarters + double-buffered
+	// scores, one CTA per SM (measured slower: 911 / 301 / 350 us -- kept selectable)
+	{ const char* e = getenv("GGML_B200_ATTN_SPLIT"); p.split = p.dual ? (e ? atoi(e) : 2) : 0; if (p.split && p.split != 4) p.split = 2; }
 	const int nt = (p.d16 > 128 || p.dual) ? 1 : 2;
-	if (p.dual) p.stages = std::min(p.stages, 2);             // two CTAs per SM: <= 113 KB each
+	if (p.dual && p.split != 4) p.stages = std::min(p.stages, 2);             // two CTAs per SM: <= 113 KB each
 	auto total = [&]() { return tile * (nt + 2 * p.stages) + 1024 + 512; };
 	while (total() > 220 * 1024 && p.stages > 1) p.stages--;
-	a->smem = total() + (p.split ? 2048 : 0);       // + the (maximum, sum) exchange of the key-split form
+	a->smem = total() + (p.split == 4 ? 4096 : p.split ? 2048 : 0);       // + the (maximum, sum) exchange of the key-split forms
 	a->grid = dim3((unsigned)((p.nq + nt * AQ - 1) / (nt * AQ)), (unsigned)p.H, (unsigned)p.B);
 	{
 		// one key block (cross-attention): CTAs walk the query tiles of their (head, image); as many CTAs per (head, image)
@@ -981,6 +1253,9 @@ void attn_tc_launch(cudaStream_t s, AttnTC* a)
 		CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute((attn_tc_kernel<64, 1, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute((attn_tc_kernel<64, 1, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute(attn_split4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute(attn_split4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute(attn_split4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute(attn_split_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute(attn_split_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute(attn_split_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
@@ -991,6 +1266,13 @@ void attn_tc_launch(cudaStream_t s, AttnTC* a)
 	if (a->kv1) {
 		if (a->p.d16 <= 64) attn_kv1_kernel<64><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
 		else attn_kv1_kernel<128><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+		g_stats.kernel_launches++;
+		return;
+	}
+	if (a->p.split == 4) {
+		if (a->p.npoly == 2) attn_split4_kernel<2><<<a->grid, 576, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+		else if (a->p.npoly == 1) attn_split4_kernel<1><<<a->grid, 576, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+		else attn_split4_kernel<0><<<a->grid, 576, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
 		g_stats.kernel_launches++;
 		return;
 	}
