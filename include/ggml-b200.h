@@ -24,6 +24,8 @@ GGML_API void* ggml_b200_malloc(size_t bytes);
 GGML_API void  ggml_b200_free(void* dev);
 GGML_API void  ggml_b200_upload(void* dev, const void* host, size_t bytes);      /* async, host buffer reusable on return */
 GGML_API void  ggml_b200_download(void* host, const void* dev, size_t bytes);    /* synchronises the engine stream */
+GGML_API void* ggml_b200_host_malloc(size_t bytes);                               /* page-locked host memory */
+GGML_API void  ggml_b200_host_free(void* p);
 GGML_API void  ggml_b200_copy(void* dst, const void* src, size_t bytes);         /* device to device */
 GGML_API void  ggml_b200_memset(void* dev, int value, size_t bytes);
 /* rows x width_bytes region copy with pitches (device to device; tile gather/scatter of the VAE tiling) */

@@ -52,7 +52,7 @@ struct MLIS_Ctx {
 	HTensor image, mask, latent, lmask, cond, label, ncond, nlabel, tmp[8];
 	float *latent_dev, *image_dev, *lmask_dev; uint8_t* u8_dev; size_t latent_dev_n, image_dev_n, lmask_dev_n, u8_dev_n;
 	bool latent_host_stale, image_host_stale;
-	MLIS_Image imgex; uint8_t* imgex_all; int img_w, img_h, img_n;
+	MLIS_Image imgex; uint8_t* imgex_all; size_t imgex_cap; int img_w, img_h, img_n;      /* imgex_all: page-locked */
 	MLIS_Progress prg; double t_last;
 	int32_t* tokens; int n_tokens, cap_tokens; float* tok_w; int cap_tok_w;
 	char* infotext;
@@ -199,7 +199,7 @@ void mlis_ctx_destroy(MLIS_Ctx** pS)
 	for (unsigned i = 0; i < 8; ++i) ht_free(ts[i]);
 	for (int i = 0; i < 8; ++i) ht_free(&S->tmp[i]);
 	free(S->backend_name); free(S->path_model); free(S->path_tae); free(S->lora_dir); free(S->aux_dir);
-	free(S->prompt_raw); free(S->nprompt_raw); free(S->tokens); free(S->tok_w); free(S->infotext); free(S->imgex_all);
+	free(S->prompt_raw); free(S->nprompt_raw); free(S->tokens); free(S->tok_w); free(S->infotext); ggml_b200_host_free(S->imgex_all);
 	free(S);
 	*pS = NULL;
 }
@@ -674,7 +674,7 @@ static int image_finish(MLIS_Ctx* S, int w, int h, int n)
 	/* float -> RGB8: clamp(v*255, 0, 255) truncated (mlimgsynth.c:112-129) */
 	if (per * n > S->u8_dev_n) { ggml_b200_free(S->u8_dev); S->u8_dev = ggml_b200_malloc(per * n); S->u8_dev_n = per * n; }
 	for (int i = 0; i < n; ++i) ggml_b200_pack_rgb8(S->u8_dev + per * i, S->image_dev + per * i, w, h, 3, 1.0f, 0.0f);
-	S->imgex_all = xrealloc(S->imgex_all, per * n);
+	if (per * n > S->imgex_cap) { ggml_b200_host_free(S->imgex_all); S->imgex_all = ggml_b200_host_malloc(per * n); S->imgex_cap = per * n; }
 	ggml_b200_download(S->imgex_all, S->u8_dev, per * n);     /* the one synchronising read of the generation */
 	S->img_w = w; S->img_h = h; S->img_n = n;
 	ht_resize(&S->image, w, h, 3, n);

@@ -146,6 +146,11 @@ extern "C" {
 
 void* ggml_b200_malloc(size_t bytes) { if (DRY) return calloc(1, bytes ? bytes : 4); void* p = nullptr; CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 4)); return p; }
 void ggml_b200_free(void* dev) { if (DRY) { free(dev); return; } if (dev) { cudaStreamSynchronize(b200_engine_stream()); cudaFree(dev); } }
+// page-locked host memory for the buffers that cross PCIe every generation (the RGB8 images): D2H at link speed, not at the
+// pageable-copy speed
+void* ggml_b200_host_malloc(size_t bytes)
+{ if (DRY) return malloc(bytes ? bytes : 4); void* p = nullptr; CUDA_CHECK(cudaMallocHost(&p, bytes ? bytes : 4)); return p; }
+void ggml_b200_host_free(void* p) { if (!p) return; if (DRY) { free(p); return; } cudaFreeHost(p); }
 void ggml_b200_upload(void* dev, const void* host, size_t bytes)
 { if (DRY) { memcpy(dev, host, bytes); return; } CUDA_CHECK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, b200_engine_stream())); g_stats.h2d_bytes += bytes; }
 void ggml_b200_download(void* host, const void* dev, size_t bytes)

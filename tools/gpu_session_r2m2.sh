@@ -3,7 +3,7 @@
 TAG=${1:-r2m2}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
-timeout 900 python -m pytest tests/test_vae_tiles_gpu.py -m gpu -q -s -k nccl 2>&1 | tail -5
+timeout 900 python -m pytest tests/test_vae_tiles_gpu.py tests/test_cfg_split_gpu.py -m gpu -q -s -k "nccl or cfg" 2>&1 | tail -8
 for n in 1 2; do
   if [ $n = 1 ]; then L="python"; else L="$TR --nproc-per-node $n --master-port 2950$n"; fi
   timeout 600 $L bench.py --gpus $n --workload c5 --steps 5 --warmup 3 > gpurun_out/bench_c5_n${n}_$TAG.json 2> gpurun_out/bench_c5_n${n}_$TAG.err; echo "c5 n=$n exit $?"; tail -c 400 gpurun_out/bench_c5_n${n}_$TAG.err
