@@ -35,7 +35,7 @@ constexpr int A_TMEM_COLS = 512;
 constexpr int A_MAX_STAGES = 4;
 
 struct AttnParams {
-	int d, d16, dchunks, nq, nk, H, B, stages, nblk, pingpong, sep_p, dual, npoly, split;
+	int d, d16, dchunks, nq, nk, H, B, stages, nblk, pingpong, sep_p, dual, npoly, split, park;
 	float scale_log2;
 	void* o; long long so_t, so_h, so_b;
 	long long* trace;     // debug timeline (tools/attn_trace.cu); null in production
@@ -413,7 +413,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 //   * the halves are merged in the epilogue through 2 KB of shared memory: O = (O_a w_a + O_b w_b) / (l_a w_a + l_b w_b).
 // Two such CTAs share an SM (256 tensor-memory columns, <= 113 KB of shared memory each): four softmax warps per SM
 // sub-partition keep the MUFU pipe fed while the others wait, load or pack.
-template <int N_POLY>
+// STAG: the two halves run in ANTI-PHASE. Each half has its own score columns' barrier (QK^T is issued as two N = 64 products),
+// its own probabilities / PV barriers, and the issuing warp serves them alternately: PV_a(j), QK_a(j+1) when half a arrives,
+// PV_b(j), QK_b(j+1) when half b arrives; half b's first product is only issued when half a has finished its first block.
+// While one half waits for the tensor pipe the other one is in its exponential pass, inside one CTA.
+template <int N_POLY, bool STAG>
 __global__ void __launch_bounds__(320, 2)
 attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
 	const AttnParams p)
@@ -430,21 +434,26 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 	uint64_t* k_empty = k_full + A_MAX_STAGES;
 	uint64_t* v_full = k_empty + A_MAX_STAGES;
 	uint64_t* v_empty = v_full + A_MAX_STAGES;
-	uint64_t* s_full = v_empty + A_MAX_STAGES;      // [1]   QK done
-	uint64_t* p_full = s_full + 1;                  // [1]   probabilities of both halves written (256 arrivals)
-	uint64_t* pv_full = p_full + 1;                 // [1]   both PV products of a block done
-	uint32_t* tmem_slot = (uint32_t*)(pv_full + 1);
+	uint64_t* s_full = v_empty + A_MAX_STAGES;      // [2]   QK done (STAG: per half)
+	uint64_t* p_full = s_full + 2;                  // [2]   probabilities written (both halves on [0], 256 arrivals; STAG: per half, 128)
+	uint64_t* pv_full = p_full + 2;                 // [2]   PV products of a block done (STAG: per half)
+	uint32_t* tmem_slot = (uint32_t*)(pv_full + 2);
 	float2* exch = (float2*)(tmem_slot + 2);        // [2 halves][128 rows] (running maximum, running sum)
 
 	const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
 	const int q0 = blockIdx.x * AQ, h = blockIdx.y, b = blockIdx.z;
+	// clock probe of one mid-run CTA (tools/attn_trace.cu): SM cycles and nanoseconds it lived, i.e. the SM clock under this kernel
+	const bool probe = p.trace && threadIdx.x == 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == gridDim.y / 2 && blockIdx.z == gridDim.z / 2;
+	long long probe_c0 = 0; unsigned long long probe_g0 = 0;
+	if (probe) { probe_c0 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(probe_g0)); }
 	constexpr uint32_t O_BASE = 128, O_STRIDE = 64;   // TMEM: S at 0 (P_a over columns [0,32), P_b over [64,96)), O_a at 128, O_b at 192
 	constexpr int W_TMA = 8, W_MMA = 9;
 
 	if (threadIdx.x == 0) {
 		tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
 		for (int s = 0; s < p.stages; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-		mbar_init(q_full, 1); mbar_init(s_full, 1); mbar_init(p_full, 256); mbar_init(pv_full, 1);
+		mbar_init(q_full, 1);
+		for (int t = 0; t < 2; ++t) { mbar_init(&s_full[t], 1); mbar_init(&p_full[t], STAG ? 128 : 256); mbar_init(&pv_full[t], 1); }
 		fence_barrier_init();
 	}
 	if (warp == W_MMA) tmem_alloc(tmem_slot, 256);
@@ -475,6 +484,56 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 		const uint64_t vdesc0 = make_smem_desc_sw128(smem_u32(sV), CHUNK_BYTES, 1024);
 		const uint32_t tile16 = (uint32_t)tile_bytes >> 4;
 		const int nk16 = p.d16 >> 4;
+		if (STAG) {
+			const uint32_t idesc_qk64 = make_idesc_f16(AQ, 64, 0, 0);
+			// S_hf = Q K(j)[64 hf .. 64 hf + 64)^T : the K tile's rows 64 hf.. are 64 * 128 B further (+512 in 16-byte units)
+			auto qk_half = [&](int j, int hf) {
+				const uint64_t bd = kdesc0 + (uint64_t)((j % p.stages) * tile16) + (uint64_t)(hf * 512);
+				#pragma unroll
+				for (int kk = 0; kk < 4; ++kk)
+					if (kk < nk16) umma_f16(tmem_base + hf * 64, qdesc0 + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc_qk64, kk ? 1u : 0u);
+				umma_commit(&s_full[hf]);
+			};
+			auto pv_half = [&](int j, int hf) {
+				const int s = j % p.stages;
+				const int valid = min(AK, p.nk - j * AK);
+				const uint64_t bd = vdesc0 + (uint64_t)(s * tile16) + (uint64_t)(hf * 512);
+				const uint32_t td = tmem_base + O_BASE + hf * O_STRIDE, ta = tmem_base + hf * 64;
+				const int nkk = (min(64, max(0, valid - hf * 64)) + 15) >> 4;
+				#pragma unroll
+				for (int kk = 0; kk < 4; ++kk)
+					if (kk < nkk) umma_f16_ts(td, ta + kk * 8, bd + (uint64_t)(kk * 128), idesc_pv, (j | kk) ? 1u : 0u);
+				umma_commit(&pv_full[hf]);
+			};
+			mbar_wait(q_full, 0);
+			mbar_wait(&k_full[0], 0);
+			tc_fence_after();
+			if (elect_one()) qk_half(0, 0);
+			__syncwarp();
+			for (int j = 0; j < p.nblk; ++j) {
+				const int s = j % p.stages;
+				const bool more = j + 1 < p.nblk;
+				mbar_wait(&v_full[s], (uint32_t)(j / p.stages) & 1);
+				if (more) mbar_wait(&k_full[(j + 1) % p.stages], (uint32_t)((j + 1) / p.stages) & 1);
+				mbar_wait(&p_full[0], (uint32_t)j & 1);
+				tc_fence_after();
+				if (elect_one()) {
+					pv_half(j, 0);
+					if (j == 0) qk_half(0, 1);               // half b starts one softmax pass behind half a
+					if (more) qk_half(j + 1, 0);
+				}
+				__syncwarp();
+				mbar_wait(&p_full[1], (uint32_t)j & 1);
+				tc_fence_after();
+				if (elect_one()) {
+					pv_half(j, 1);
+					umma_commit(&v_empty[s]);
+					umma_commit(&k_empty[s]);                // QK_a(j) and QK_b(j) were issued before this point
+					if (more) qk_half(j + 1, 1);
+				}
+				__syncwarp();
+			}
+		} else {
 		// The issuing warp is the critical path between the softmax of block j and that of block j + 1 (PV(j), then QK(j+1)
 		// into the same score columns). Everything that can be waited for early is waited for BEFORE the probabilities
 		// arrive (V(j) and K(j+1) resident); after p_full only one fence and one elected section remain.
@@ -485,7 +544,7 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 			#pragma unroll
 			for (int kk = 0; kk < 4; ++kk)
 				if (kk < nk16) umma_f16(tmem_base, qdesc0 + (uint64_t)(kk * 2), kdesc0 + (uint64_t)(kk * 2), idesc_qk, kk ? 1u : 0u);
-			umma_commit(s_full);
+			umma_commit(&s_full[0]);
 			umma_commit(&k_empty[0]);
 			ATTN_TR(2, 0, 3);
 		}
@@ -497,7 +556,7 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 			mbar_wait(&v_full[s], (uint32_t)(j / p.stages) & 1);
 			if (more) mbar_wait(&k_full[s1], (uint32_t)((j + 1) / p.stages) & 1);
 			if (lane == 0) ATTN_TR(3, j, 4);
-			mbar_wait(p_full, (uint32_t)j & 1);
+			mbar_wait(&p_full[0], (uint32_t)j & 1);
 			tc_fence_after();
 			if (elect_one()) {
 				ATTN_TR(2, j, 1);
@@ -512,7 +571,7 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 					for (int kk = 0; kk < 4; ++kk)
 						if (kk < nkk) umma_f16_ts(td, ta + kk * 8, bd + (uint64_t)(kk * 128), idesc_pv, (j | kk) ? 1u : 0u);
 				}
-				umma_commit(pv_full);
+				umma_commit(&pv_full[0]);
 				umma_commit(&v_empty[s]);
 				ATTN_TR(2, j, 2);
 				if (more) {                              // in order after both products: S / P may be overwritten
@@ -520,12 +579,13 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 					#pragma unroll
 					for (int kk = 0; kk < 4; ++kk)
 						if (kk < nk16) umma_f16(tmem_base, qdesc0 + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc_qk, kk ? 1u : 0u);
-					umma_commit(s_full);
+					umma_commit(&s_full[0]);
 					umma_commit(&k_empty[s1]);
 					ATTN_TR(2, j + 1, 3);
 				}
 			}
 			__syncwarp();
+		}
 		}
 	} else {
 		// ===== softmax: warp = quarter (TMEM lanes) + 4 * half (key columns); one (row, half) per thread =====
@@ -538,12 +598,13 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 		float m = -INFINITY, l = 0.f;
 		bool first = true;
 		const bool tr = quarter == 0 && lane == 0;
+		const int hb = STAG ? hf : 0;                     // barrier set of this thread
 
 		auto block = [&](int j, auto full_tag) {
 			constexpr bool FULL = decltype(full_tag)::value;
 			const int valid = FULL ? 64 : min(64, max(0, p.nk - j * AK - hf * 64));      // valid keys of my half
 			if (tr) ATTN_TR(hf, j, 0);
-			mbar_wait_parked(s_full, (uint32_t)j & 1);
+			mbar_wait_parked(&s_full[hb], (uint32_t)j & 1);
 			tc_fence_after();
 			if (tr) ATTN_TR(hf, j, 1);
 			uint32_t va[32], vb[32];
@@ -551,7 +612,7 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 				#pragma unroll
 				for (int i = 0; i < 16; ++i) va[i] = 0u;
 				tmem_st16(ts, va); tmem_st16(ts + 16, va);
-				tmem_st_wait(); tc_fence_before(); mbar_arrive(p_full);
+				tmem_st_wait(); tc_fence_before(); mbar_arrive(&p_full[hb]);
 				return;
 			}
 			tmem_ld32(ts, va); tmem_ld32(ts + 32, vb);
@@ -587,7 +648,7 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 					const float corr = ex2_approx(m - m_new);
 					m = m_new;
 					l *= corr;
-					mbar_wait(pv_full, (uint32_t)(j - 1) & 1);     // the PV products so far have landed in O
+					mbar_wait(&pv_full[hb], (uint32_t)(j - 1) & 1);     // the PV products so far have landed in O
 					tc_fence_after();
 					#pragma unroll
 					for (int c0 = 0; c0 < 64; c0 += 16) {
@@ -631,7 +692,7 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 			if (tr) ATTN_TR(hf, j, 4);
 			tmem_st_wait();
 			tc_fence_before();
-			mbar_arrive(p_full);
+			mbar_arrive(&p_full[hb]);
 			if (tr) ATTN_TR(hf, j, 5);
 		};
 		const int nfull = p.nk / AK;      // a partial block can only be the last one
@@ -640,7 +701,8 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
 		// epilogue: merge the halves. Every thread publishes (m, l) of its (row, half), then takes the 16-column chunks
 		// c with (c & 1) == half of BOTH accumulators of its row.
-		mbar_wait(pv_full, (uint32_t)(p.nblk - 1) & 1);
+		mbar_wait(&pv_full[0], (uint32_t)(p.nblk - 1) & 1);
+		if (STAG) mbar_wait(&pv_full[1], (uint32_t)(p.nblk - 1) & 1);
 		tc_fence_after();
 		exch[hf * 128 + r] = make_float2(m, l);
 		named_bar_sync(1, 256);
@@ -686,6 +748,7 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 	}
 	tc_fence_before();
 	__syncthreads();
+	if (probe) { unsigned long long g1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1)); p.trace[2046] = clock64() - probe_c0; p.trace[2047] = (long long)(g1 - probe_g0); }
 	if (warp == W_MMA) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
 }
 
@@ -702,8 +765,9 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 // tcgen05.ld), its own running maximum / sum, and writes 16 packed probability columns over the start of its own scores. The
 // warps of a sub-partition only meet at the MUFU pipe: four of them per sub-partition keep it fed while others load, pack or wait.
 // Epilogue: the four partial (m, l, O) of a row are merged through 4 KB of shared memory.
-template <int N_POLY>
-__global__ void __launch_bounds__(576, 1)
+// NKQ key parts per block (4: sixteen softmax warps, 32 scores per thread; 2: eight softmax warps, 64 scores per thread)
+template <int N_POLY, int NKQ>
+__global__ void __launch_bounds__(128 * NKQ + 64, 1)
 attn_split4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
 	const AttnParams p)
 {
@@ -720,7 +784,7 @@ attn_split4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 	uint64_t* v_full = k_empty + A_MAX_STAGES;
 	uint64_t* v_empty = v_full + A_MAX_STAGES;
 	uint64_t* s_full = v_empty + A_MAX_STAGES;      // [2]   QK into score buffer b done
-	uint64_t* p_full = s_full + 2;                  // [2]   probabilities of buffer b written (512 arrivals)
+	uint64_t* p_full = s_full + 2;                  // [2]   probabilities of buffer b written (128 NKQ arrivals)
 	uint64_t* pv_full = p_full + 2;                 // [1]   PV products of a block done
 	uint32_t* tmem_slot = (uint32_t*)(pv_full + 1);
 	float2* exch = (float2*)(tmem_slot + 2);        // [4 quarters][128 rows] (running maximum, running sum)
@@ -728,13 +792,14 @@ attn_split4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 	const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
 	const int q0 = blockIdx.x * AQ, h = blockIdx.y, b = blockIdx.z;
 	constexpr uint32_t O_BASE = 256, O_STRIDE = 64;
-	constexpr int W_TMA = 16, W_MMA = 17;
+	constexpr int W_TMA = 4 * NKQ, W_MMA = 4 * NKQ + 1;
+	constexpr int EPT = 128 / NKQ;                   // scores per thread and block
 
 	if (threadIdx.x == 0) {
 		tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
 		for (int s = 0; s < p.stages; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
 		mbar_init(q_full, 1); mbar_init(pv_full, 1);
-		for (int t = 0; t < 2; ++t) { mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 512); }
+		for (int t = 0; t < 2; ++t) { mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 128 * NKQ); }
 		fence_barrier_init();
 	}
 	if (warp == W_MMA) tmem_alloc(tmem_slot, 512);
@@ -800,12 +865,12 @@ attn_split4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 				// V tile: rows = keys (128 B each), 16 keys further = +16 * 128 B; quarter q starts 32 keys * q in.
 				// P in tensor memory: 16 keys = 8 packed 32-bit columns, quarter q's probabilities start at column 32 q of S[j & 1].
 				#pragma unroll
-				for (int q = 0; q < 4; ++q) {
-					const uint64_t bd = vdesc0 + (uint64_t)(s * tile16) + (uint64_t)(q * 256);
-					const uint32_t td = tmem_base + O_BASE + q * O_STRIDE, ta = tmem_base + (uint32_t)(j & 1) * 128 + q * 32;
-					const int nkk = (min(32, max(0, valid - q * 32)) + 15) >> 4;
+				for (int q = 0; q < NKQ; ++q) {
+					const uint64_t bd = vdesc0 + (uint64_t)(s * tile16) + (uint64_t)(q * EPT * 8);
+					const uint32_t td = tmem_base + O_BASE + q * O_STRIDE, ta = tmem_base + (uint32_t)(j & 1) * 128 + q * EPT;
+					const int nkk = (min(EPT, max(0, valid - q * EPT)) + 15) >> 4;
 					#pragma unroll
-					for (int kk = 0; kk < 2; ++kk)
+					for (int kk = 0; kk < EPT / 16; ++kk)
 						if (kk < nkk) umma_f16_ts(td, ta + kk * 8, bd + (uint64_t)(kk * 128), idesc_pv, (j | kk) ? 1u : 0u);
 				}
 				umma_commit(pv_full);
@@ -819,7 +884,7 @@ attn_split4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 		const int kq = warp >> 2, lg = warp & 3;
 		const int r = lg * 32 + lane;
 		const uint32_t lane_off = (uint32_t)(lg * 32) << 16;
-		const uint32_t ts0 = tmem_base + lane_off + kq * 32;                     // my 32 scores in buffer 0 (+128 for buffer 1)
+		const uint32_t ts0 = tmem_base + lane_off + kq * EPT;                    // my EPT scores in buffer 0 (+128 for buffer 1)
 		const uint32_t to = tmem_base + O_BASE + kq * O_STRIDE + lane_off;       // my quarter's output accumulator of this row
 		const float sl2 = p.scale_log2;
 		float m = -INFINITY, l = 0.f;
@@ -827,24 +892,26 @@ attn_split4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
 		auto block = [&](int j, auto full_tag) {
 			constexpr bool FULL = decltype(full_tag)::value;
-			const int valid = FULL ? 32 : min(32, max(0, p.nk - j * AK - kq * 32));      // valid keys of my quarter
+			const int valid = FULL ? EPT : min(EPT, max(0, p.nk - j * AK - kq * EPT));      // valid keys of my part
 			const uint32_t ts = ts0 + (uint32_t)(j & 1) * 128;
-			mbar_wait_parked(&s_full[j & 1], (uint32_t)(j >> 1) & 1);
+			if (p.park) mbar_wait_parked(&s_full[j & 1], (uint32_t)(j >> 1) & 1); else mbar_wait(&s_full[j & 1], (uint32_t)(j >> 1) & 1);
 			tc_fence_after();
-			uint32_t v[32];
-			if (!FULL && valid <= 0) {                                           // nothing of this block belongs to my quarter
+			uint32_t v[EPT];
+			if (!FULL && valid <= 0) {                                           // nothing of this block belongs to my part
 				#pragma unroll
 				for (int i = 0; i < 16; ++i) v[i] = 0u;
-				tmem_st16(ts, v);
+				#pragma unroll
+				for (int c = 0; c < EPT / 32; ++c) tmem_st16(ts + c * 16, v);
 				tmem_st_wait(); tc_fence_before(); mbar_arrive(&p_full[j & 1]);
 				return;
 			}
-			tmem_ld32(ts, v);
+			#pragma unroll
+			for (int c = 0; c < EPT / 32; ++c) tmem_ld32(ts + c * 32, v + c * 32);
 			tmem_ld_wait();
 			float mx4[4] = { -INFINITY, -INFINITY, -INFINITY, -INFINITY };
 			if (FULL) {
 				#pragma unroll
-				for (int i = 0; i < 32; i += 8) {
+				for (int i = 0; i < EPT; i += 8) {
 					mx4[0] = max3f(mx4[0], __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
 					mx4[1] = max3f(mx4[1], __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
 					mx4[2] = max3f(mx4[2], __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
@@ -852,7 +919,7 @@ attn_split4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 				}
 			} else {
 				#pragma unroll
-				for (int i = 0; i < 32; ++i) if (i < valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
+				for (int i = 0; i < EPT; ++i) if (i < valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
 			}
 			const float m_blk = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sl2;
 			// Lazy rescaling (as above): keep the old maximum while the block maximum exceeds it by < 2^8.
@@ -883,9 +950,9 @@ attn_split4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 			}
 			const float mneg = -m;
 			float rs4[4] = { 0.f, 0.f, 0.f, 0.f };
-			uint32_t packed[16];
+			uint32_t packed[EPT / 2];
 			#pragma unroll
-			for (int i = 0; i < 32; i += 2) {
+			for (int i = 0; i < EPT; i += 2) {
 				float e0, e1;
 				{ const float xs = fmaf(__uint_as_float(v[i]), sl2, mneg); e0 = (i & 7) < N_POLY ? ex2_poly(xs) : ex2_approx(xs); }
 				{ const float xs = fmaf(__uint_as_float(v[i + 1]), sl2, mneg); e1 = ((i + 1) & 7) < N_POLY ? ex2_poly(xs) : ex2_approx(xs); }
@@ -894,7 +961,8 @@ attn_split4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 				__half2 hh = __floats2half2_rn(e0, e1);
 				packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
 			}
-			tmem_st16(ts, packed);
+			#pragma unroll
+			for (int c = 0; c < EPT / 32; ++c) tmem_st16(ts + c * 16, packed + c * 16);
 			l += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
 			tmem_st_wait();
 			tc_fence_before();
@@ -909,22 +977,23 @@ attn_split4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 		mbar_wait(pv_full, (uint32_t)(p.nblk - 1) & 1);
 		tc_fence_after();
 		exch[kq * 128 + r] = make_float2(first ? -INFINITY : m, l);
-		named_bar_sync(1, 512);
-		float mq[4], lq[4], M = -INFINITY;
+		named_bar_sync(1, 128 * NKQ);
+		float mq[NKQ], lq[NKQ], M = -INFINITY;
 		#pragma unroll
-		for (int q = 0; q < 4; ++q) { const float2 e = exch[q * 128 + r]; mq[q] = e.x; lq[q] = e.y; M = fmaxf(M, e.x); }
-		float wq[4], L = 0.f;
+		for (int q = 0; q < NKQ; ++q) { const float2 e = exch[q * 128 + r]; mq[q] = e.x; lq[q] = e.y; M = fmaxf(M, e.x); }
+		float wq[NKQ], L = 0.f;
 		#pragma unroll
-		for (int q = 0; q < 4; ++q) { wq[q] = (mq[q] == -INFINITY) ? 0.f : ex2_approx(mq[q] - M); L += lq[q] * wq[q]; }
+		for (int q = 0; q < NKQ; ++q) { wq[q] = (mq[q] == -INFINITY) ? 0.f : ex2_approx(mq[q] - M); L += lq[q] * wq[q]; }
 		const float inv = L > 0.f ? 1.0f / L : 0.f;
-		const int c0 = kq * 16;
+		#pragma unroll
+		for (int c0 = kq * 16; c0 < 64; c0 += NKQ * 16)       // 16-column chunk c of the output is merged by part c % NKQ
 		if (c0 < p.d16) {
 			const long long tok = (long long)q0 + r;
 			float o[16];
 			#pragma unroll
 			for (int i = 0; i < 16; ++i) o[i] = 0.f;
 			#pragma unroll
-			for (int q = 0; q < 4; ++q) {
+			for (int q = 0; q < NKQ; ++q) {
 				uint32_t oq[16];
 				tmem_ld16(tmem_base + O_BASE + q * O_STRIDE + lane_off + c0, oq);
 				tmem_ld_wait();
@@ -1200,9 +1269,11 @@ AttnTC* attn_tc_prepare(const View& o, const View& q, const View& k, const View&
 	p.trace = nullptr;
 	{ const char* e = getenv("GGML_B200_ATTN_PP"); p.pingpong = e ? atoi(e) : 1; }
 	{ const char* e = getenv("GGML_B200_ATTN_SEP"); p.sep_p = e ? atoi(e) : 0; }
+	{ const char* e = getenv("GGML_B200_ATTN_PARK"); p.park = e ? atoi(e) : 1; }       // long waits parked with a suspend-time hint (0: polled)
 	// dual form: one exponential in eight on the FMA pipe (measured -4 % at d = 40, -2.6 % at d = 64; two in eight is worse)
-	{ const char* e = getenv("GGML_B200_ATTN_POLY"); p.npoly = e ? atoi(e) : 1; }
-	p.d = (int)q.ne[0]; p.d16 = (p.d + 15) / 16 * 16; p.dchunks = (p.d + ACH - 1) / ACH;
+	p.d = (int)q.ne[0]; p.d16 = (p.d + 15) / 16 * 16;
+	{ const char* e = getenv("GGML_B200_ATTN_POLY"); p.npoly = e ? atoi(e) : (p.d16 > 48 && p.d16 <= 64 ? 0 : 1); }
+	p.d16 = (p.d + 15) / 16 * 16; p.dchunks = (p.d + ACH - 1) / ACH;
 	p.nq = (int)q.ne[1]; p.nk = (int)k.ne[1]; p.H = (int)q.ne[2]; p.B = (int)q.ne[3];
 	p.nblk = (p.nk + AK - 1) / AK;
 	p.scale_log2 = scale * 1.4426950408889634f;
@@ -1215,12 +1286,12 @@ AttnTC* attn_tc_prepare(const View& o, const View& q, const View& k, const View&
 	// GGML_B200_ATTN_SPLIT: 0 = one row per thread (round-1 dual form), 2 = key halves, two CTAs per SM (default: 837 / 272 / 340 us on
 	// the three shapes of profiles/r2_attention_microbench.md against 841 / 300 / 392 us), 4 = key quarters + double-buffered
 	// scores, one CTA per SM (measured slower: 911 / 301 / 350 us -- kept selectable)
-	{ const char* e = getenv("GGML_B200_ATTN_SPLIT"); p.split = p.dual ? (e ? atoi(e) : 2) : 0; if (p.split && p.split != 4) p.split = 2; }
+	{ const char* e = getenv("GGML_B200_ATTN_SPLIT"); p.split = p.dual ? (e ? atoi(e) : 2) : 0; if (p.split && p.split != 4 && p.split != 3) p.split = 2; }
 	const int nt = (p.d16 > 128 || p.dual) ? 1 : 2;
-	if (p.dual && p.split != 4) p.stages = std::min(p.stages, 2);             // two CTAs per SM: <= 113 KB each
+	if (p.dual && p.split != 4 && p.split != 3) p.stages = std::min(p.stages, 2);             // two CTAs per SM: <= 113 KB each
 	auto total = [&]() { return tile * (nt + 2 * p.stages) + 1024 + 512; };
 	while (total() > 220 * 1024 && p.stages > 1) p.stages--;
-	a->smem = total() + (p.split == 4 ? 4096 : p.split ? 2048 : 0);       // + the (maximum, sum) exchange of the key-split forms
+	a->smem = total() + (p.split >= 3 ? 4096 : p.split ? 2048 : 0);       // + the (maximum, sum) exchange of the key-split forms
 	a->grid = dim3((unsigned)((p.nq + nt * AQ - 1) / (nt * AQ)), (unsigned)p.H, (unsigned)p.B);
 	{
 		// one key block (cross-attention): CTAs walk the query tiles of their (head, image); as many CTAs per (head, image)
@@ -1253,12 +1324,17 @@ void attn_tc_launch(cudaStream_t s, AttnTC* a)
 		CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute((attn_tc_kernel<64, 1, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute((attn_tc_kernel<64, 1, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-		CUDA_CHECK(cudaFuncSetAttribute(attn_split4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-		CUDA_CHECK(cudaFuncSetAttribute(attn_split4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-		CUDA_CHECK(cudaFuncSetAttribute(attn_split4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-		CUDA_CHECK(cudaFuncSetAttribute(attn_split_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-		CUDA_CHECK(cudaFuncSetAttribute(attn_split_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-		CUDA_CHECK(cudaFuncSetAttribute(attn_split_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute((attn_split4_kernel<0, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute((attn_split4_kernel<1, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute((attn_split4_kernel<2, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute((attn_split4_kernel<0, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute((attn_split4_kernel<1, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute((attn_split_kernel<0, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute((attn_split_kernel<1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute((attn_split_kernel<2, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute((attn_split_kernel<0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute((attn_split_kernel<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute((attn_split_kernel<2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute(attn_kv1_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute(attn_kv1_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		attr_set = true;
@@ -1270,16 +1346,32 @@ void attn_tc_launch(cudaStream_t s, AttnTC* a)
 		return;
 	}
 	if (a->p.split == 4) {
-		if (a->p.npoly == 2) attn_split4_kernel<2><<<a->grid, 576, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
-		else if (a->p.npoly == 1) attn_split4_kernel<1><<<a->grid, 576, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
-		else attn_split4_kernel<0><<<a->grid, 576, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+		if (a->p.npoly == 2) attn_split4_kernel<2, 4><<<a->grid, 576, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+		else if (a->p.npoly == 1) attn_split4_kernel<1, 4><<<a->grid, 576, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+		else attn_split4_kernel<0, 4><<<a->grid, 576, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+		g_stats.kernel_launches++;
+		return;
+	}
+	if (a->p.split == 3) {          // key halves + double-buffered scores, one CTA per SM
+		if (a->p.npoly >= 1) attn_split4_kernel<1, 2><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+		else attn_split4_kernel<0, 2><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
 		g_stats.kernel_launches++;
 		return;
 	}
 	if (a->p.split) {
-		if (a->p.npoly == 2) attn_split_kernel<2><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
-		else if (a->p.npoly == 1) attn_split_kernel<1><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
-		else attn_split_kernel<0><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+		// measured (profiles/r2_attention_microbench.md): 64-wide heads gain 4-6 % from the anti-phase halves with all exponentials on
+		// the MUFU pipe; 40-wide heads (one MMA fewer per product) are 1 % faster in phase with one exponential in eight on the FMA pipe
+		static const int stag_env = getenv("GGML_B200_ATTN_STAGGER") ? atoi(getenv("GGML_B200_ATTN_STAGGER")) : -1;
+		const bool stag = stag_env >= 0 ? stag_env != 0 : a->p.d16 > 48;
+		if (stag) {
+			if (a->p.npoly == 2) attn_split_kernel<2, true><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+			else if (a->p.npoly == 1) attn_split_kernel<1, true><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+			else attn_split_kernel<0, true><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+		} else {
+			if (a->p.npoly == 2) attn_split_kernel<2, false><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+			else if (a->p.npoly == 1) attn_split_kernel<1, false><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+			else attn_split_kernel<0, false><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+		}
 		g_stats.kernel_launches++;
 		return;
 	}

@@ -48,6 +48,7 @@ int main(int argc, char** argv)
 	attn_tc_launch(s, a); CUDA_CHECK(cudaStreamSynchronize(s));
 	std::vector<long long> ht(4 * 64 * 8);
 	CUDA_CHECK(cudaMemcpy(ht.data(), tr, ht.size() * 8, cudaMemcpyDeviceToHost));
+	if (ht[2047] > 0) printf("clock probe (mid-run CTA): %lld cycles in %lld ns -> SM clock %.0f MHz under this kernel\n", ht[2046], ht[2047], 1e3 * (double)ht[2046] / (double)ht[2047]);
 	long long t0 = ht[(2 * 64 + 0) * 8 + 3];     // first QK issue
 	auto T = [&](int role, int j, int ev) { long long x = ht[(role * 64 + j) * 8 + ev]; return x ? (long long)(x - t0) : -1; };
 	printf("softmax events: 0 wait_s  1 s_ready  2 max_done  3 turn  4 exp_done  5 p_arrived ; mma: 0 pv_wait 1 p_ready 2 pv_issued 3 qk_issued (per tile)\n");

@@ -7,6 +7,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > g
 timeout 1500 python -m pytest tests -m gpu -q -s -rs > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_$TAG.log
 grep -a "passed\|failed\|^FAILED" gpurun_out/pytest_$TAG.log | tail -5
 timeout 1200 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench exit $?"
+timeout 900 python bench.py --workload c3 --steps 1 --warmup 3 > gpurun_out/bench_c3_n1_$TAG.json 2> gpurun_out/bench_c3_n1_$TAG.err; echo "c3 n=1 exit $?"
 L=$(python -c "import json;d=json.load(open('gpurun_out/bench_$TAG.json'));print(d['gpu_launches']//d['steps'])")
 G=$(python -c "import json;d=json.load(open('gpurun_out/bench_$TAG.json'));print(d['roofline']['launches_per_unet_eval'])")
 echo "launches per generation: $L, gemm launches per UNet evaluation: $G"
