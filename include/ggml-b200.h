@@ -57,6 +57,11 @@ GGML_API void ggml_b200_box_downsample(float* out, const float* in, int w, int h
 
 /* LoRA merge on device (lora.c:46-78): W[n1][n0] (f16) <- f16( f32(W) + scale * (up[n1][r] . down[r][n0]) ),
  * operands f16, products accumulated in f32, ONE f16 rounding per merge (same as the reference). */
+/* Ordered merge of decoded tiles (all geometry in OUTPUT pixels): tile t = t1 * nt0 + t0 starts at min(t0 * step0, ow - tw) and keeps
+ * [margin, margin + tw - margin) of its extent (margin 0 at the origin; the whole extent when one tile covers the axis); every pixel takes the last
+ * tile of the row-major list that covers it; tile t lives at slot (t % world) * slots + t / world of `tiles`; out = (v + pre_add) * mul. */
+GGML_API void ggml_b200_tile_merge(float* out, const float* tiles, int ow, int oh, int planes, int nt0, int nt1, int tw, int th, int step0, int step1,
+	int keep_margin, int full0, int full1, int world, int slots, float pre_add, float mul);
 GGML_API void ggml_b200_lora_merge_f16(void* w_dev, const void* down_dev, const void* up_dev, int64_t n0, int64_t n1, int r, float scale);
 GGML_API void ggml_b200_lora_merge_f32(void* w_dev, const void* down_dev, const void* up_dev, int64_t n0, int64_t n1, int r, float scale);
 

@@ -255,17 +255,13 @@ int sdvae_merge_tiles(const VaeParams* P, int lw, int lh, int tile_px, const flo
 	const int nt = sdvae_tile_plan(P, lw, lh, tile_px, &T);
 	const int f = T.f, k = T.k, ow = lw * f, oh = lh * f, tw_o = T.n0 * f, th_o = T.n1 * f;
 	if (world < 1 || slots_per_worker * world < nt) FAIL(-1, "tile buffer too small: %d x %d slots for %d tiles", world, slots_per_worker, nt);
-	for (int t = 0; t < nt; ++t) {            /* the reference's order: t1 outer, t0 inner */
-		int t1 = t / T.nt0, t0 = t % T.nt0;
-		int i1 = t1 * T.step1; if (i1 > lh - T.n1) i1 = lh - T.n1;
-		int i0 = t0 * T.step0; if (i0 > lw - T.n0) i0 = lw - T.n0;
-		const float* tout = gathered_dev + T.tile_elems * ((size_t)(t % world) * slots_per_worker + t / world);
-		if (nt == 1) { copy_region(image_dev, ow, oh, 0, 0, tout, tw_o, th_o, 0, 0, tw_o, th_o, P->ch_x); break; }
-		int d0 = i0 ? k : 0, d1 = i1 ? k : 0;
-		int c0 = T.n0 == lw ? T.n0 : T.n0 - k, c1 = T.n1 == lh ? T.n1 : T.n1 - k;      /* same kept region as run_tiled */
-		copy_region(image_dev, ow, oh, (i0 + d0) * f, (i1 + d1) * f, tout, tw_o, th_o, d0 * f, d1 * f, c0 * f, c1 * f, P->ch_x);
-	}
-	ggml_b200_affine(image_dev, image_dev, 1, 0.5f, 0, (int64_t)ow * oh * P->ch_x);   /* (x+1)/2 (vae.h:43-47) */
+	/* one launch: every output pixel takes the LAST tile of the reference's row-major list (t1 outer, t0 inner) whose kept region
+	   covers it -- exactly what pasting the tiles one after the other produces (vae.c:365-387) -- and (x+1)/2 is applied on the way
+	   (vae.h:43-47). Kept region of a tile, in latent pixels: [d, d + n - k) with d = k except at the origin; a dim that one tile covers
+	   entirely is copied whole (same rule as run_tiled). */
+	(void)nt;
+	ggml_b200_tile_merge(image_dev, gathered_dev, ow, oh, P->ch_x, T.nt0, T.nt1, tw_o, th_o, T.step0 * f, T.step1 * f, k * f,
+		T.n0 == lw, T.n1 == lh, world, slots_per_worker, 1.0f, 0.5f);
 	return nt;
 }
 

@@ -108,6 +108,38 @@ __global__ void box_downsample_kernel(float* out, const float* in, int w, int h,
 	out[i] = s / (fw * fh);
 }
 
+// Ordered merge of decoded VAE tiles (vae.c:365-387): every output pixel takes the LAST tile of the reference's row-major list whose kept
+// region covers it (later tiles overwrite earlier ones), then out = (v + pre_add) * mul. One launch instead of one 2-D copy per tile and plane.
+struct TileMergeArgs {
+	int ow, oh, planes, nt0, nt1, tw, th, step0, step1, n0f, n1f, kf, full0, full1, world, slots;
+	long long tile_elems; float pre_add, mul;
+};
+__host__ __device__ inline void tile_merge_pixel(const TileMergeArgs& a, const float* tiles, float* out, int x, int y)
+{
+	// candidate tile columns / rows: walk backwards, the first hit is the last writer
+	int t0 = -1, t1 = -1, sx = 0, sy = 0;
+	for (int t = a.nt0 - 1; t >= 0 && t0 < 0; --t) {
+		int i0 = t * a.step0; if (i0 > a.ow - a.n0f) i0 = a.ow - a.n0f;
+		const int d0 = i0 ? a.kf : 0, c0 = a.full0 ? a.n0f : a.n0f - a.kf;
+		if (x >= i0 + d0 && x < i0 + d0 + c0) { t0 = t; sx = x - i0; }
+	}
+	for (int t = a.nt1 - 1; t >= 0 && t1 < 0; --t) {
+		int i1 = t * a.step1; if (i1 > a.oh - a.n1f) i1 = a.oh - a.n1f;
+		const int d1 = i1 ? a.kf : 0, c1 = a.full1 ? a.n1f : a.n1f - a.kf;
+		if (y >= i1 + d1 && y < i1 + d1 + c1) { t1 = t; sy = y - i1; }
+	}
+	if (t0 < 0 || t1 < 0) return;          // (not covered: cannot happen for a valid plan; the pixel keeps its value)
+	const int t = t1 * a.nt0 + t0;
+	const float* src = tiles + a.tile_elems * ((long long)(t % a.world) * a.slots + t / a.world);
+	for (int p = 0; p < a.planes; ++p)
+		out[((long long)p * a.oh + y) * a.ow + x] = (src[((long long)p * a.th + sy) * a.tw + sx] + a.pre_add) * a.mul;
+}
+__global__ void tile_merge_kernel(TileMergeArgs a, const float* __restrict__ tiles, float* __restrict__ out)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+	if (x < a.ow) tile_merge_pixel(a, tiles, out, x, y);
+}
+
 __device__ __forceinline__ float lora_ld(const __half* p) { return __half2float(*p); }
 __device__ __forceinline__ float lora_ld(const float* p) { return *p; }
 __device__ __forceinline__ void lora_st(__half* p, float v) { *p = __float2half_rn(v); }
@@ -229,6 +261,18 @@ void ggml_b200_box_downsample(float* out, const float* in, int w, int h, int pla
 	if (DRY) return;
 	long long total = (long long)(w / fw) * (h / fh) * planes;
 	box_downsample_kernel<<<nblk(total, 256), 256, 0, b200_engine_stream()>>>(out, in, w, h, planes, fw, fh);
+	g_stats.kernel_launches++;
+}
+void ggml_b200_tile_merge(float* out, const float* tiles, int ow, int oh, int planes, int nt0, int nt1, int tw, int th, int step0, int step1,
+	int keep_margin, int full0, int full1, int world, int slots, float pre_add, float mul)
+{
+	TileMergeArgs a = { ow, oh, planes, nt0, nt1, tw, th, step0, step1, tw, th, keep_margin, full0, full1, world, slots, (long long)planes * tw * th, pre_add, mul };
+	if (DRY) {          // host buffers: the same per-pixel rule (CPU tests of the merge order)
+		for (int y = 0; y < oh; ++y) for (int x = 0; x < ow; ++x) tile_merge_pixel(a, tiles, out, x, y);
+		return;
+	}
+	dim3 grid(nblk(ow, 256), (unsigned)oh);
+	tile_merge_kernel<<<grid, 256, 0, b200_engine_stream()>>>(a, tiles, out);
 	g_stats.kernel_launches++;
 }
 void ggml_b200_lora_merge_f16(void* w_dev, const void* down_dev, const void* up_dev, int64_t n0, int64_t n1, int r, float scale)

@@ -86,6 +86,7 @@ def _dryrun_merge_worker(q):
     tw, th = plan.n0 * 8, plan.n1 * 8
     tiles = [_fake_tile(i, tw, th) for i in range(nt)]
     want, n_ref, tile_px = _serial_reference(LW, LH, TILE_PX, tiles)
+    want = (want + np.float32(1)) * np.float32(0.5)             # the merge applies the decoder's (x+1)/2 on the way (vae.h:43-47)
     ok = (nt == n_ref == 35) and tile_px == (tw, th) and plan.tile_elems == 3 * tw * th
     for world in (1, 2, 3, 8):
         slots = (nt + world - 1) // world
@@ -130,6 +131,7 @@ def _worker(rank, world, port, q):
         if rank == 0:
             got, n = _merge_with_product(L, P, np.stack(g), world, slots)
             want, _, _ = _serial_reference(LW, LH, TILE_PX, [_fake_tile(t, tw, th) for t in range(nt)])
+            want = (want + np.float32(1)) * np.float32(0.5)
             ok = n == nt and np.array_equal(got, want) and (got != 0).all()
             # the Python mirrors of the geometry (used for planning / docs) agree with the C plan
             ok = ok and len(D.tile_list(LW, LH, plan.n0, plan.n1, 8)) == nt
