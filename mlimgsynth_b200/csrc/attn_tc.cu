@@ -35,7 +35,7 @@ constexpr int A_TMEM_COLS = 512;
 constexpr int A_MAX_STAGES = 4;
 
 struct AttnParams {
-	int d, d16, dchunks, nq, nk, H, B, stages, nblk, pingpong, sep_p, dual, npoly, split, park;
+	int d, d16, dchunks, nq, nk, H, B, stages, nblk, pingpong, sep_p, dual, npoly, split, park, pk, sig;
 	float scale_log2;
 	void* o; long long so_t, so_h, so_b;
 	long long* trace;     // debug timeline (tools/attn_trace.cu); null in production
@@ -73,6 +73,35 @@ __device__ __forceinline__ float ex2_poly(float x)
 
 __device__ __forceinline__ float max3f(float a, float b, float c)
 { float y; asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c)); return y; }
+
+// Packed f32x2 arithmetic (sm_100: FFMA2 / FADD2 take ONE issue slot for two elements). The softmax of narrow heads is bound by
+// issue slots as much as by the MUFU pipe (profiles/r2_attention_microbench.md), so the scale-and-subtract, the row sums and the
+// polynomial exponentials run on register pairs.
+__device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ uint64_t pk2u(uint32_t a, uint32_t b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ void unpk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
+{ uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+// ex2_poly on a register pair: the clamp and the exponent insertion stay scalar (no packed min/max or integer forms), the
+// rounding, the reduction and the polynomial are packed: 10 issue slots per pair against 2 MUFU.EX2 (16 MUFU cycles per warp).
+__device__ __forceinline__ void ex2_poly2(uint64_t x2, float& e0, float& e1)
+{
+	float x0, x1; unpk2(x2, x0, x1);
+	x0 = fmaxf(x0, -126.0f); x1 = fmaxf(x1, -126.0f);
+	const uint64_t xc = pk2(x0, x1);
+	const uint64_t xr = add2(xc, pk2(12582912.0f, 12582912.0f));
+	const uint64_t n = sub2(xr, pk2(12582912.0f, 12582912.0f));
+	const uint64_t f = sub2(xc, n);
+	uint64_t q = fma2(f, pk2(0.0551716648f, 0.0551716648f), pk2(0.242611125f, 0.242611125f));
+	q = fma2(q, f, pk2(0.693260968f, 0.693260968f));
+	q = fma2(q, f, pk2(0.999928057f, 0.999928057f));
+	float q0, q1, r0, r1; unpk2(q, q0, q1); unpk2(xr, r0, r1);
+	e0 = __int_as_float(__float_as_int(q0) + (__float_as_int(r0) << 23));
+	e1 = __int_as_float(__float_as_int(q1) + (__float_as_int(r1) << 23));
+}
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(n) : "memory"); }
@@ -417,7 +446,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 // its own probabilities / PV barriers, and the issuing warp serves them alternately: PV_a(j), QK_a(j+1) when half a arrives,
 // PV_b(j), QK_b(j+1) when half b arrives; half b's first product is only issued when half a has finished its first block.
 // While one half waits for the tensor pipe the other one is in its exponential pass, inside one CTA.
-template <int N_POLY, bool STAG>
+// PK: 0 = scalar softmax arithmetic (round-2 form, N_POLY of every 8 exponentials on the FMA pipe);
+//     1 = packed f32x2 arithmetic (FFMA2 scale-and-subtract, FADD2 row sums, packed polynomial: N_POLY PAIRS of every 8 pairs);
+//     2 = packed, and the row sums come from the TENSOR CORE: every PV product is followed by a product of the same probabilities
+//         with a tile of ones (N = 16) into 16 tensor-memory columns right of the half's accumulator, so the sum is taken over the
+//         f16-rounded probabilities that the PV product really used, and the softmax loop holds no additions at all. Needs
+//         d16 + 16 <= 64 columns per half (heads up to 48 wide: SD1.x level 0).
+template <int N_POLY, bool STAG, int PK = 0>
 __global__ void __launch_bounds__(320, 2)
 attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
 	const AttnParams p)
@@ -428,7 +463,8 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 	uint8_t* sQ = smem;
 	uint8_t* sK = sQ + tile_bytes;
 	uint8_t* sV = sK + (size_t)p.stages * tile_bytes;
-	uint64_t* bars = (uint64_t*)(sV + (size_t)p.stages * tile_bytes);
+	uint8_t* sOnes = sV + (size_t)p.stages * tile_bytes;             // PK == 2: 16 key rows of 128 B, every f16 = 1.0 (any swizzle of it is itself)
+	uint64_t* bars = (uint64_t*)(sOnes + (PK == 2 ? 2048 : 0));
 	uint64_t* q_full = bars;                        // [1]
 	uint64_t* k_full = q_full + 1;                  // [stages]
 	uint64_t* k_empty = k_full + A_MAX_STAGES;
@@ -455,6 +491,10 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 		mbar_init(q_full, 1);
 		for (int t = 0; t < 2; ++t) { mbar_init(&s_full[t], 1); mbar_init(&p_full[t], STAG ? 128 : 256); mbar_init(&pv_full[t], 1); }
 		fence_barrier_init();
+	}
+	if (PK == 2) {
+		if (threadIdx.x < 128) reinterpret_cast<uint4*>(sOnes)[threadIdx.x] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+		fence_proxy_async();
 	}
 	if (warp == W_MMA) tmem_alloc(tmem_slot, 256);
 	tc_fence_before();
@@ -484,6 +524,8 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 		const uint64_t vdesc0 = make_smem_desc_sw128(smem_u32(sV), CHUNK_BYTES, 1024);
 		const uint32_t tile16 = (uint32_t)tile_bytes >> 4;
 		const int nk16 = p.d16 >> 4;
+		const uint32_t idesc_sum = make_idesc_f16(AQ, 16, 0, 1);                     // PK == 2: row sums = P x ones
+		const uint64_t odesc = make_smem_desc_sw128(smem_u32(sOnes), CHUNK_BYTES, 1024);
 		if (STAG) {
 			const uint32_t idesc_qk64 = make_idesc_f16(AQ, 64, 0, 0);
 			// S_hf = Q K(j)[64 hf .. 64 hf + 64)^T : the K tile's rows 64 hf.. are 64 * 128 B further (+512 in 16-byte units)
@@ -570,6 +612,11 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 					#pragma unroll
 					for (int kk = 0; kk < 4; ++kk)
 						if (kk < nkk) umma_f16_ts(td, ta + kk * 8, bd + (uint64_t)(kk * 128), idesc_pv, (j | kk) ? 1u : 0u);
+					if (PK == 2) {
+						#pragma unroll
+						for (int kk = 0; kk < 4; ++kk)
+							if (kk < nkk) umma_f16_ts(td + p.d16, ta + kk * 8, odesc, idesc_sum, (j | kk) ? 1u : 0u);
+					}
 				}
 				umma_commit(&pv_full[0]);
 				umma_commit(&v_empty[s]);
@@ -597,7 +644,7 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 		const float sl2 = p.scale_log2;
 		float m = -INFINITY, l = 0.f;
 		bool first = true;
-		const bool tr = quarter == 0 && lane == 0;
+		const bool tr = PK == 0 && quarter == 0 && lane == 0;     // timeline probe (tools/attn_trace.cu): scalar form only
 		const int hb = STAG ? hf : 0;                     // barrier set of this thread
 
 		auto block = [&](int j, auto full_tag) {
@@ -652,7 +699,7 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 					tc_fence_after();
 					#pragma unroll
 					for (int c0 = 0; c0 < 64; c0 += 16) {
-						if (c0 < p.d16) {
+						if (c0 < p.d16 + (PK == 2 ? 16 : 0)) {                   // PK == 2: the sum columns follow the accumulator
 							uint32_t o[16];
 							tmem_ld16(to + c0, o);
 							tmem_ld_wait();
@@ -665,30 +712,53 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 			}
 			const float mneg = -m;
 			if (tr) ATTN_TR(hf, j, 3);
-			float rs4[4] = { 0.f, 0.f, 0.f, 0.f };
-			auto exps = [&](uint32_t* v, int c) {
-				#pragma unroll
-				for (int i = 0; i < 32; ++i) {
-					const float xs = fmaf(__uint_as_float(v[i]), sl2, mneg);
-					float e = (i & 7) < N_POLY ? ex2_poly(xs) : ex2_approx(xs);
-					if (!FULL) { if (c * 32 + i >= valid) e = 0.f; }
-					v[i] = __float_as_uint(e);
-				}
-			};
-			auto finish = [&](const uint32_t* v, int c) {
-				uint32_t packed[16];
-				#pragma unroll
-				for (int i = 0; i < 32; i += 2) {
-					const float p0 = __uint_as_float(v[i]), p1 = __uint_as_float(v[i + 1]);
-					rs4[(i >> 1) & 3] += p0 + p1;
-					__half2 hh = __floats2half2_rn(p0, p1);
-					packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
-				}
-				tmem_st16(ts + c * 16, packed);
-			};
-			exps(va, 0); exps(vb, 1);
-			finish(va, 0); finish(vb, 1);
-			l += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+			if constexpr (PK > 0) {
+				const uint64_t SL = pk2(sl2, sl2), MN = pk2(mneg, mneg);
+				uint64_t acc0 = 0ull, acc1 = 0ull;
+				auto pass = [&](uint32_t* v, int c) {
+					uint32_t packed[16];
+					#pragma unroll
+					for (int i = 0; i < 32; i += 2) {
+						const int pi = i >> 1;
+						const uint64_t x2 = fma2(pk2u(v[i], v[i + 1]), SL, MN);
+						float e0, e1;
+						if (N_POLY > 0 && (((pi & 7) * N_POLY) & 7) < N_POLY) ex2_poly2(x2, e0, e1);
+						else { float x0, x1; unpk2(x2, x0, x1); e0 = ex2_approx(x0); e1 = ex2_approx(x1); }
+						if (!FULL) { if (c * 32 + i >= valid) e0 = 0.f; if (c * 32 + i + 1 >= valid) e1 = 0.f; }
+						if (PK == 1) { if (pi & 1) acc1 = add2(acc1, pk2(e0, e1)); else acc0 = add2(acc0, pk2(e0, e1)); }
+						__half2 hh = __floats2half2_rn(e0, e1);
+						packed[pi] = *reinterpret_cast<uint32_t*>(&hh);
+					}
+					tmem_st16(ts + c * 16, packed);
+				};
+				pass(va, 0); pass(vb, 1);
+				if (PK == 1) { float a0, a1; unpk2(add2(acc0, acc1), a0, a1); l += a0 + a1; }
+			} else {
+				float rs4[4] = { 0.f, 0.f, 0.f, 0.f };
+				auto exps = [&](uint32_t* v, int c) {
+					#pragma unroll
+					for (int i = 0; i < 32; ++i) {
+						const float xs = fmaf(__uint_as_float(v[i]), sl2, mneg);
+						float e = (i & 7) < N_POLY ? ex2_poly(xs) : ex2_approx(xs);
+						if (!FULL) { if (c * 32 + i >= valid) e = 0.f; }
+						v[i] = __float_as_uint(e);
+					}
+				};
+				auto finish = [&](const uint32_t* v, int c) {
+					uint32_t packed[16];
+					#pragma unroll
+					for (int i = 0; i < 32; i += 2) {
+						const float p0 = __uint_as_float(v[i]), p1 = __uint_as_float(v[i + 1]);
+						rs4[(i >> 1) & 3] += p0 + p1;
+						__half2 hh = __floats2half2_rn(p0, p1);
+						packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+					}
+					tmem_st16(ts + c * 16, packed);
+				};
+				exps(va, 0); exps(vb, 1);
+				finish(va, 0); finish(vb, 1);
+				l += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+			}
 			if (tr) ATTN_TR(hf, j, 4);
 			tmem_st_wait();
 			tc_fence_before();
@@ -704,6 +774,12 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 		mbar_wait(&pv_full[0], (uint32_t)(p.nblk - 1) & 1);
 		if (STAG) mbar_wait(&pv_full[1], (uint32_t)(p.nblk - 1) & 1);
 		tc_fence_after();
+		if (PK == 2) {                                   // the row sum of my half: any of the 16 columns right of the accumulator
+			uint32_t t16[16];
+			tmem_ld16(to + p.d16, t16);
+			tmem_ld_wait();
+			l = __uint_as_float(t16[0]);
+		}
 		exch[hf * 128 + r] = make_float2(m, l);
 		named_bar_sync(1, 256);
 		const float2 oth = exch[(hf ^ 1) * 128 + r];
@@ -1028,6 +1104,334 @@ attn_split4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 
+// ------------------------------------------------------------------ heads up to 64 wide: two query tiles in ENFORCED anti-phase
+// What bounds the forms above (timelines in profiles/r2_attention_microbench.md, r3_attention.md): a softmax warp alternates between
+// a phase without exponentials (wait for the scores, tcgen05.ld, row maximum, later pack + tcgen05.st + the round trip through the
+// issuing warp and the tensor pipe: PV(j), QK(j+1)) and a phase that is nothing but exponentials. Warps that share a barrier run
+// these phases together, so the MUFU pipe idles during the first and is oversubscribed during the second (45-55 % busy).
+// Here ONE CTA per SM owns TWO tiles of 128 query rows (streams A, B: warps 0-3 / 4-7, one row per thread) and walks the keys in
+// blocks of 64:
+//   * scores are DOUBLE-BUFFERED per stream (2 x 64 tensor-memory columns): QK(u+2) is issued right behind PV(u), so the scores
+//     of the next block are complete long before a stream asks for them -- the tensor-pipe round trip leaves the critical path;
+//   * the two warps of an SM sub-partition (stream A's and stream B's) hand the MUFU pipe to each other through named barriers:
+//     B starts the exponentials of its block u when A has issued the signal of its block u, A starts block u+1 on B's signal
+//     (p.sig: 1 = signal half-way through the exponentials, 2 = at their end, 0 = free-running). While one stream is in its
+//     exponential phase the other loads, takes the maximum, packs and stores;
+//   * packed f32x2 arithmetic, N_POLY pairs of every 8 pairs as polynomial on the FMA pipe;
+//   * SUMMMA: the row sums come from the tensor core (P x ones, N = 16, into the 16 columns right of the accumulator).
+// Tensor memory: S_A[2] 0..127, S_B[2] 128..255, O_A 256..335, O_B 336..415 (d16 + 16 <= 80 columns each).
+constexpr int AP_KST = 3, AP_VST = 3;
+#ifdef ATTN_AP_TRACE
+#define AP_TR(role, j, ev) ATTN_TR(role, j, ev)
+#else
+#define AP_TR(role, j, ev) do { } while (0)
+#endif
+template <int N_POLY, bool SUMMMA, int NK16>
+__global__ void __launch_bounds__(352, 1)
+attn_ap_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+	const AttnParams p)
+{
+	extern __shared__ __align__(1024) uint8_t smem_raw[];
+	uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+	constexpr int TB = CHUNK_BYTES;                  // d <= 64: one 128-byte chunk per row, 128 rows
+	uint8_t* sQ = smem;                              // [2 tiles]
+	uint8_t* sK = sQ + 2 * TB;                       // [AP_KST] tiles of 128 keys
+	uint8_t* sV = sK + AP_KST * TB;                  // [AP_VST]
+	uint8_t* sOnes = sV + AP_VST * TB;               // 16 key rows of 128 B, every f16 = 1.0
+	uint64_t* bars = (uint64_t*)(sOnes + 2048);
+	uint64_t* q_full = bars;                         // [2]
+	uint64_t* k_full = q_full + 2;                   // [AP_KST]
+	uint64_t* k_empty = k_full + AP_KST;
+	uint64_t* v_full = k_empty + AP_KST;             // [AP_VST]
+	uint64_t* v_empty = v_full + AP_VST;
+	uint64_t* s_full = v_empty + AP_VST;             // [2 streams][2 buffers]  QK done
+	uint64_t* p_full = s_full + 4;                   // [2][2]  probabilities written (128 arrivals)
+	uint64_t* pv_full = p_full + 4;                  // [2]     PV product of a block done
+	uint32_t* tmem_slot = (uint32_t*)(pv_full + 2);
+
+	const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
+	const int q0 = blockIdx.x * (2 * AQ), h = blockIdx.y, b = blockIdx.z;
+	constexpr uint32_t O_BASE = 256, O_STRIDE = 80;
+	constexpr int W_TMA = 8, W_MMA = 9;
+	constexpr int BAR_A2B = 2, BAR_B2A = 6;          // named barriers 2..5 / 6..9: one pair per SM sub-partition
+	const int n64 = (p.nk + 63) >> 6;                // key blocks of 64 (>= 3: single-tile contexts run attn_kv1_kernel)
+
+	if (threadIdx.x == 0) {
+		tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+		for (int s = 0; s < AP_KST; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 2); }      // freed by both streams
+		for (int s = 0; s < AP_VST; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 2); }
+		for (int t = 0; t < 2; ++t) { mbar_init(&q_full[t], 1); mbar_init(&pv_full[t], 1); }
+		for (int t = 0; t < 4; ++t) { mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 128); }
+		fence_barrier_init();
+	}
+	if (SUMMMA) {
+		if (threadIdx.x < 128) reinterpret_cast<uint4*>(sOnes)[threadIdx.x] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+		fence_proxy_async();
+	}
+	if (warp == W_MMA) tmem_alloc(tmem_slot, 512);
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = uniform_u32(*tmem_slot);
+
+	if (warp == W_TMA) {
+		if (lane == 0) {
+			auto load_k = [&](int j) {
+				const int s = j % AP_KST; const uint32_t ph = (uint32_t)(j / AP_KST) & 1;
+				mbar_wait_parked(&k_empty[s], ph ^ 1);
+				mbar_expect_tx(&k_full[s], TB);
+				tma_load_4d(sK + (size_t)s * TB, &tmK, &k_full[s], 0, j * AK, h, b);
+			};
+			auto load_v = [&](int j) {
+				const int s = j % AP_VST; const uint32_t ph = (uint32_t)(j / AP_VST) & 1;
+				mbar_wait_parked(&v_empty[s], ph ^ 1);
+				mbar_expect_tx(&v_full[s], TB);
+				tma_load_4d(sV + (size_t)s * TB, &tmV, &v_full[s], 0, j * AK, h, b);
+			};
+			mbar_expect_tx(&q_full[0], TB);
+			tma_load_4d(sQ, &tmQ, &q_full[0], 0, q0, h, b);
+			load_k(0);
+			mbar_expect_tx(&q_full[1], TB);
+			tma_load_4d(sQ + TB, &tmQ, &q_full[1], 0, q0 + AQ, h, b);
+			// K runs one tile ahead of V: QK(u+2) is issued together with PV(u)
+			for (int j = 0; j < p.nblk; ++j) { if (j + 1 < p.nblk) load_k(j + 1); load_v(j); }
+		}
+	} else if (warp >= W_MMA) {
+		// ===== one issuing warp PER STREAM (a single issuing thread for both was the bottleneck: ~1500 clk per pair of blocks,
+		// profiles/r3_attention.md). Straight-line issue for full blocks: K-steps are compile-time (NK16), descriptors precomputed.
+		const int t = warp - W_MMA;
+		const int nk16 = NK16 ? NK16 : (p.d16 >> 4);
+		const uint32_t idesc_qk = make_idesc_f16(AQ, 64, 0, 0);
+		const uint32_t idesc_pv = make_idesc_f16(AQ, p.d16, 0, 1);     // A = P (TMEM), B = V MN-major ([key][d], d contiguous)
+		const uint32_t idesc_sum = make_idesc_f16(AQ, 16, 0, 1);
+		constexpr uint32_t tile16 = (uint32_t)TB >> 4;
+		const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ), 16, 1024) + (uint64_t)(t * tile16);
+		const uint64_t kdesc0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+		const uint64_t vdesc0 = make_smem_desc_sw128(smem_u32(sV), CHUNK_BYTES, 1024);
+		const uint64_t odesc = make_smem_desc_sw128(smem_u32(sOnes), CHUNK_BYTES, 1024);
+		const uint32_t t_s = tmem_base + (uint32_t)(t * 128), t_o = tmem_base + O_BASE + (uint32_t)t * O_STRIDE;
+		// S_t[u & 1] = Q_t K[64 u .. 64 u + 64)^T : K tile u >> 1 in ring slot ks, rows 64 (u & 1).. (+8 KB = +512 in 16-byte units)
+		auto qk = [&](int u, int ks) {
+			const uint64_t bd = kdesc0 + (uint64_t)(ks * tile16) + (uint64_t)((u & 1) * 512);
+			const uint32_t td = t_s + (uint32_t)((u & 1) * 64);
+			#pragma unroll
+			for (int kk = 0; kk < 4; ++kk)
+				if (kk < nk16) umma_f16(td, qdesc + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc_qk, kk ? 1u : 0u);
+			umma_commit(&s_full[t * 2 + (u & 1)]);
+			if ((u & 1) || u == n64 - 1) umma_commit(&k_empty[ks]);          // this stream is done with the K tile (2 arrivals free it)
+		};
+		// O_t += P_t(u) V[64 u ..): P = 32 packed columns over the start of S_t[u & 1]; 16 keys = 8 columns of P, 16 rows of V
+		auto pv = [&](int u, int vs, auto full_tag) {
+			constexpr bool FULL = decltype(full_tag)::value;
+			const int nkk = FULL ? 4 : ((min(64, p.nk - u * 64) + 15) >> 4);
+			const uint64_t bd = vdesc0 + (uint64_t)(vs * tile16) + (uint64_t)((u & 1) * 512);
+			const uint32_t ta = t_s + (uint32_t)((u & 1) * 64);
+			const uint32_t acc = u ? 1u : 0u;
+			#pragma unroll
+			for (int kk = 0; kk < 4; ++kk)
+				if (FULL || kk < nkk) umma_f16_ts(t_o, ta + kk * 8, bd + (uint64_t)(kk * 128), idesc_pv, kk ? 1u : acc);
+			if (SUMMMA) {
+				#pragma unroll
+				for (int kk = 0; kk < 4; ++kk)
+					if (FULL || kk < nkk) umma_f16_ts(t_o + p.d16, ta + kk * 8, odesc, idesc_sum, kk ? 1u : acc);
+			}
+			umma_commit(&pv_full[t]);
+			if ((u & 1) || u == n64 - 1) umma_commit(&v_empty[vs]);
+		};
+		mbar_wait(&q_full[t], 0);
+		mbar_wait(&k_full[0], 0);
+		tc_fence_after();
+		if (elect_one()) { qk(0, 0); qk(1, 0); }
+		__syncwarp();
+		const int nfull = p.nk >> 6;
+		int ks = 1 % AP_KST, vs = 0;                  // ring slots of K tile j + 1 and V tile j (j = u >> 1)
+		uint32_t kph = 0, vph = 0;
+		for (int u = 0; u < n64; ++u) {
+			const bool more = u + 2 < n64;
+			if (!(u & 1)) {
+				mbar_wait(&v_full[vs], vph);
+				if (more) mbar_wait(&k_full[ks], kph);
+			}
+			mbar_wait(&p_full[t * 2 + (u & 1)], (uint32_t)(u >> 1) & 1);
+			tc_fence_after();
+			if (elect_one()) {
+				AP_TR(2, u, t * 4 + 0);
+				if (u < nfull) pv(u, vs, std::true_type{}); else pv(u, vs, std::false_type{});
+				AP_TR(2, u, t * 4 + 1);
+				if (more) qk(u + 2, ks);               // in order behind PV(u): S_t[u & 1] / P_t(u) may be overwritten
+				AP_TR(2, u, t * 4 + 2);
+			}
+			__syncwarp();
+			if (u & 1) {
+				if (++ks == AP_KST) { ks = 0; kph ^= 1; }
+				if (++vs == AP_VST) { vs = 0; vph ^= 1; }
+			}
+		}
+	} else {
+		// ===== softmax: stream t = warp / 4 (query tile), TMEM lane group = warp % 4; one query row per thread =====
+		const int t = warp >> 2, quarter = warp & 3;
+		const int r = quarter * 32 + lane;
+		const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+		const uint32_t ts0 = tmem_base + lane_off + (uint32_t)t * 128;
+		const uint32_t to = tmem_base + O_BASE + (uint32_t)t * O_STRIDE + lane_off;
+		const float sl2 = p.scale_log2;
+		const int sig = p.sig;
+		float m = -INFINITY, l = 0.f;
+#ifdef ATTN_AP_TRACE
+		const bool tr = p.trace != nullptr && quarter == 0 && lane == 0;      // timeline probe (tools/attn_trace.cu, -DATTN_AP_TRACE builds only)
+#else
+		constexpr bool tr = false;
+#endif
+
+		auto block = [&](int u, auto full_tag) {
+			constexpr bool FULL = decltype(full_tag)::value;
+			const int valid = FULL ? 64 : p.nk - u * 64;                       // 1..63 in the partial (last) block
+			const uint32_t ts = ts0 + (uint32_t)(u & 1) * 64;
+			if (tr) ATTN_TR(t, u, 0);
+			mbar_wait_parked(&s_full[t * 2 + (u & 1)], (uint32_t)(u >> 1) & 1);
+			tc_fence_after();
+			if (tr) ATTN_TR(t, u, 1);
+			uint32_t va[32], vb[32];
+			tmem_ld32(ts, va); tmem_ld32(ts + 32, vb);
+			tmem_ld_wait();
+			if (tr) ATTN_TR(t, u, 2);
+			float mx4[4] = { -INFINITY, -INFINITY, -INFINITY, -INFINITY };
+			if (FULL) {
+				#pragma unroll
+				for (int i = 0; i < 32; i += 8) {
+					mx4[0] = max3f(mx4[0], __uint_as_float(va[i]), __uint_as_float(va[i + 1]));
+					mx4[1] = max3f(mx4[1], __uint_as_float(va[i + 2]), __uint_as_float(va[i + 3]));
+					mx4[2] = max3f(mx4[2], __uint_as_float(va[i + 4]), __uint_as_float(va[i + 5]));
+					mx4[3] = max3f(mx4[3], __uint_as_float(va[i + 6]), __uint_as_float(va[i + 7]));
+					mx4[0] = max3f(mx4[0], __uint_as_float(vb[i]), __uint_as_float(vb[i + 1]));
+					mx4[1] = max3f(mx4[1], __uint_as_float(vb[i + 2]), __uint_as_float(vb[i + 3]));
+					mx4[2] = max3f(mx4[2], __uint_as_float(vb[i + 4]), __uint_as_float(vb[i + 5]));
+					mx4[3] = max3f(mx4[3], __uint_as_float(vb[i + 6]), __uint_as_float(vb[i + 7]));
+				}
+			} else {
+				#pragma unroll
+				for (int i = 0; i < 32; ++i) {
+					if (i < valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(va[i]));
+					if (32 + i < valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(vb[i]));
+				}
+			}
+			const float m_blk = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sl2;
+			// Lazy rescaling: keep the old maximum while the block maximum exceeds it by < 2^8 (f16 probabilities stay < 2^8 x 1).
+			if (u == 0) m = m_blk;
+			else {
+				const bool need = m_blk > m + 8.0f;
+				if (__any_sync(0xffffffffu, need)) {
+					const float m_new = need ? m_blk : m;
+					const float corr = ex2_approx(m - m_new);
+					m = m_new;
+					l *= corr;
+					mbar_wait(&pv_full[t], (uint32_t)(u - 1) & 1);       // PV(u-1) has landed; PV(u) cannot be in flight yet
+					tc_fence_after();
+					#pragma unroll
+					for (int c0 = 0; c0 < 80; c0 += 16) {
+						if (c0 < p.d16 + (SUMMMA ? 16 : 0)) {
+							uint32_t o[16];
+							tmem_ld16(to + c0, o);
+							tmem_ld_wait();
+							#pragma unroll
+							for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+							tmem_st16(to + c0, o);
+						}
+					}
+				}
+			}
+			if (tr) ATTN_TR(t, u, 3);
+			// my turn on the MUFU pipe
+			if (sig) {
+				if (t == 0) { if (u > 0) named_bar_sync(BAR_B2A + quarter, 64); }
+				else named_bar_sync(BAR_A2B + quarter, 64);
+			}
+			auto signal = [&]() {
+				if (t == 0) named_bar_arrive(BAR_A2B + quarter, 64);
+				else if (u + 1 < n64) named_bar_arrive(BAR_B2A + quarter, 64);
+			};
+			if (tr) ATTN_TR(t, u, 4);
+			const uint64_t SL = pk2(sl2, sl2), MN = pk2(-m, -m);
+			uint64_t acc0 = 0ull, acc1 = 0ull;
+			auto pass = [&](uint32_t* v, int c) {
+				uint32_t packed[16];
+				#pragma unroll
+				for (int i = 0; i < 32; i += 2) {
+					const int pi = i >> 1;
+					const uint64_t x2 = fma2(pk2u(v[i], v[i + 1]), SL, MN);
+					float e0, e1;
+					if (N_POLY > 0 && (((pi & 7) * N_POLY) & 7) < N_POLY) ex2_poly2(x2, e0, e1);
+					else { float x0, x1; unpk2(x2, x0, x1); e0 = ex2_approx(x0); e1 = ex2_approx(x1); }
+					if (!FULL) { if (c * 32 + i >= valid) e0 = 0.f; if (c * 32 + i + 1 >= valid) e1 = 0.f; }
+					if (!SUMMMA) { if (pi & 1) acc1 = add2(acc1, pk2(e0, e1)); else acc0 = add2(acc0, pk2(e0, e1)); }
+					__half2 hh = __floats2half2_rn(e0, e1);
+					packed[pi] = *reinterpret_cast<uint32_t*>(&hh);
+				}
+				tmem_st16(ts + c * 16, packed);
+			};
+			pass(va, 0);
+			if (sig == 1) signal();
+			pass(vb, 1);
+			if (sig == 2) signal();
+			if (!SUMMMA) { float a0, a1; unpk2(add2(acc0, acc1), a0, a1); l += a0 + a1; }
+			if (tr) ATTN_TR(t, u, 5);
+			tmem_st_wait();
+			tc_fence_before();
+			if (tr) ATTN_TR(t, u, 6);
+			mbar_arrive(&p_full[t * 2 + (u & 1)]);
+		};
+		const int nfull = p.nk >> 6;          // a partial block can only be the last one
+		for (int u = 0; u < nfull; ++u) block(u, std::true_type{});
+		if (nfull < n64) block(nfull, std::false_type{});
+
+		// epilogue: O / l -> f16 -> global memory
+		// the scores are double-buffered, so this thread may be TWO products ahead of the tensor pipe: a parity wait alone cannot
+		// tell phase n64 - 1 from n64 - 3; PV(n64 - 3) is known complete (QK(n64 - 1) completed behind it), so wait phase by phase
+		mbar_wait(&pv_full[t], (uint32_t)(n64 - 2) & 1);
+		mbar_wait(&pv_full[t], (uint32_t)(n64 - 1) & 1);
+		tc_fence_after();
+		if (SUMMMA) {
+			uint32_t t16[16];
+			tmem_ld16(to + p.d16, t16);
+			tmem_ld_wait();
+			l = __uint_as_float(t16[0]);
+		}
+		const float inv = l > 0.f ? 1.0f / l : 0.f;
+		const long long tok = (long long)q0 + t * AQ + r;
+		__half* op = (__half*)p.o + tok * p.so_t + (long long)h * p.so_h + (long long)b * p.so_b;
+		const bool vec = ((((uintptr_t)op) & 15) == 0);
+		#pragma unroll
+		for (int c0 = 0; c0 < 64; c0 += 16) {
+			if (c0 < p.d16) {
+				uint32_t oa[16];
+				tmem_ld16(to + c0, oa);
+				tmem_ld_wait();
+				if (tok < p.nq) {
+					#pragma unroll
+					for (int h8 = 0; h8 < 16; h8 += 8) {
+						const int cc = c0 + h8;
+						if (cc < p.d) {
+							if (vec && cc + 8 <= p.d) {
+								uint4 o4; __half2* hp = reinterpret_cast<__half2*>(&o4);
+								#pragma unroll
+								for (int i = 0; i < 4; ++i) hp[i] = __floats2half2_rn(__uint_as_float(oa[h8 + 2 * i]) * inv, __uint_as_float(oa[h8 + 2 * i + 1]) * inv);
+								*reinterpret_cast<uint4*>(op + cc) = o4;
+							} else {
+								#pragma unroll
+								for (int i = 0; i < 8; ++i) if (cc + i < p.d) op[cc + i] = __float2half_rn(__uint_as_float(oa[h8 + i]) * inv);
+							}
+						}
+					}
+				}
+			}
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == W_MMA) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+
 // ------------------------------------------------------------------ single key block (cross-attention, nk <= 128)
 // The text context of a cross-attention has 77 keys (unet.c:110-145): one key block. With one (pair of) query tile(s)
 // per CTA such a launch is a chain of latencies -- load, QK^T, softmax, PV, store -- that nothing overlaps, ~6 us per
@@ -1286,12 +1690,28 @@ AttnTC* attn_tc_prepare(const View& o, const View& q, const View& k, const View&
 	// GGML_B200_ATTN_SPLIT: 0 = one row per thread (round-1 dual form), 2 = key halves, two CTAs per SM (default: 837 / 272 / 340 us on
 	// the three shapes of profiles/r2_attention_microbench.md against 841 / 300 / 392 us), 4 = key quarters + double-buffered
 	// scores, one CTA per SM (measured slower: 911 / 301 / 350 us -- kept selectable)
-	{ const char* e = getenv("GGML_B200_ATTN_SPLIT"); p.split = p.dual ? (e ? atoi(e) : 2) : 0; if (p.split && p.split != 4 && p.split != 3) p.split = 2; }
-	const int nt = (p.d16 > 128 || p.dual) ? 1 : 2;
-	if (p.dual && p.split != 4 && p.split != 3) p.stages = std::min(p.stages, 2);             // two CTAs per SM: <= 113 KB each
+	{ const char* e = getenv("GGML_B200_ATTN_SPLIT"); p.split = p.dual ? (e ? atoi(e) : 2) : 0; if (p.split && p.split != 4 && p.split != 3 && p.split != 5) p.split = 2; }
+	const int nt = (p.d16 > 128 || (p.dual && p.split != 5)) ? 1 : 2;
+	if (p.dual && p.split != 4 && p.split != 3 && p.split != 5) p.stages = std::min(p.stages, 2);             // two CTAs per SM: <= 113 KB each
 	auto total = [&]() { return tile * (nt + 2 * p.stages) + 1024 + 512; };
 	while (total() > 220 * 1024 && p.stages > 1) p.stages--;
 	a->smem = total() + (p.split >= 3 ? 4096 : p.split ? 2048 : 0);       // + the (maximum, sum) exchange of the key-split forms
+	// packed softmax arithmetic of the key-halves form (GGML_B200_ATTN_PK: 0 scalar, 1 packed, 2 packed + row sums on the tensor core)
+	{
+		const char* e = getenv("GGML_B200_ATTN_PK");
+		p.pk = p.split == 2 ? (e ? atoi(e) : 0) : 0;
+		if (p.pk == 2 && p.d16 > 48) p.pk = 1;
+		if (p.pk == 2) a->smem += 2048;
+		if (p.pk) { const char* ep = getenv("GGML_B200_ATTN_POLY"); p.npoly = std::max(0, std::min(4, ep ? atoi(ep) : 2)); }
+	}
+	p.sig = 0;
+	if (p.split == 5) {          // two query tiles per CTA in enforced anti-phase (attn_ap_kernel)
+		const char* e = getenv("GGML_B200_ATTN_PK"); p.pk = e ? atoi(e) : 2;
+		if (p.pk != 1) p.pk = 2;
+		const char* ep = getenv("GGML_B200_ATTN_POLY"); p.npoly = std::max(0, std::min(3, ep ? atoi(ep) : 2));
+		const char* es = getenv("GGML_B200_ATTN_SIG"); p.sig = es ? atoi(es) : 1;
+		a->smem = (size_t)(2 + AP_KST + AP_VST) * CHUNK_BYTES + 2048 + 1024 + 1024;
+	}
 	a->grid = dim3((unsigned)((p.nq + nt * AQ - 1) / (nt * AQ)), (unsigned)p.H, (unsigned)p.B);
 	{
 		// one key block (cross-attention): CTAs walk the query tiles of their (head, image); as many CTAs per (head, image)
@@ -1335,6 +1755,21 @@ void attn_tc_launch(cudaStream_t s, AttnTC* a)
 		CUDA_CHECK(cudaFuncSetAttribute((attn_split_kernel<0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute((attn_split_kernel<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute((attn_split_kernel<2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+		#define PK_ATTR(NP) \
+			CUDA_CHECK(cudaFuncSetAttribute((attn_split_kernel<NP, false, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024)); \
+			CUDA_CHECK(cudaFuncSetAttribute((attn_split_kernel<NP, true, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024)); \
+			CUDA_CHECK(cudaFuncSetAttribute((attn_split_kernel<NP, false, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+		PK_ATTR(0) PK_ATTR(1) PK_ATTR(2) PK_ATTR(3) PK_ATTR(4)
+		#undef PK_ATTR
+		#define AP_ATTR(NP) \
+			CUDA_CHECK(cudaFuncSetAttribute((attn_ap_kernel<NP, true, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+			CUDA_CHECK(cudaFuncSetAttribute((attn_ap_kernel<NP, true, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+			CUDA_CHECK(cudaFuncSetAttribute((attn_ap_kernel<NP, true, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+			CUDA_CHECK(cudaFuncSetAttribute((attn_ap_kernel<NP, false, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+			CUDA_CHECK(cudaFuncSetAttribute((attn_ap_kernel<NP, false, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+			CUDA_CHECK(cudaFuncSetAttribute((attn_ap_kernel<NP, false, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		AP_ATTR(0) AP_ATTR(1) AP_ATTR(2) AP_ATTR(3)
+		#undef AP_ATTR
 		CUDA_CHECK(cudaFuncSetAttribute(attn_kv1_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute(attn_kv1_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		attr_set = true;
@@ -1342,6 +1777,17 @@ void attn_tc_launch(cudaStream_t s, AttnTC* a)
 	if (a->kv1) {
 		if (a->p.d16 <= 64) attn_kv1_kernel<64><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
 		else attn_kv1_kernel<128><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
+		g_stats.kernel_launches++;
+		return;
+	}
+	if (a->p.split == 5) {
+		#define AP_K(NP, SM, K16) attn_ap_kernel<NP, SM, K16><<<a->grid, 352, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p)
+		#define AP_SM(NP, SM) do { if (a->p.d16 == 48) AP_K(NP, SM, 3); else if (a->p.d16 == 64) AP_K(NP, SM, 4); else AP_K(NP, SM, 0); } while (0)
+		#define AP_CASE(NP) do { if (a->p.pk == 2) AP_SM(NP, true); else AP_SM(NP, false); } while (0)
+		switch (a->p.npoly) { case 0: AP_CASE(0); break; case 1: AP_CASE(1); break; case 2: AP_CASE(2); break; default: AP_CASE(3); break; }
+		#undef AP_CASE
+		#undef AP_SM
+		#undef AP_K
 		g_stats.kernel_launches++;
 		return;
 	}
@@ -1363,7 +1809,16 @@ void attn_tc_launch(cudaStream_t s, AttnTC* a)
 		// the MUFU pipe; 40-wide heads (one MMA fewer per product) are 1 % faster in phase with one exponential in eight on the FMA pipe
 		static const int stag_env = getenv("GGML_B200_ATTN_STAGGER") ? atoi(getenv("GGML_B200_ATTN_STAGGER")) : -1;
 		const bool stag = stag_env >= 0 ? stag_env != 0 : a->p.d16 > 48;
-		if (stag) {
+		if (a->p.pk) {
+			#define PK_CASE(NP, ST, PKV) attn_split_kernel<NP, ST, PKV><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p)
+			#define PK_NP(ST, PKV) switch (a->p.npoly) { case 0: PK_CASE(0, ST, PKV); break; case 1: PK_CASE(1, ST, PKV); break; \
+				case 2: PK_CASE(2, ST, PKV); break; case 3: PK_CASE(3, ST, PKV); break; default: PK_CASE(4, ST, PKV); break; }
+			if (a->p.pk == 2) { PK_NP(false, 2) }
+			else if (stag) { PK_NP(true, 1) }
+			else { PK_NP(false, 1) }
+			#undef PK_NP
+			#undef PK_CASE
+		} else if (stag) {
 			if (a->p.npoly == 2) attn_split_kernel<2, true><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
 			else if (a->p.npoly == 1) attn_split_kernel<1, true><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);
 			else attn_split_kernel<0, true><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p);

@@ -51,6 +51,20 @@ int main(int argc, char** argv)
 	if (ht[2047] > 0) printf("clock probe (mid-run CTA): %lld cycles in %lld ns -> SM clock %.0f MHz under this kernel\n", ht[2046], ht[2047], 1e3 * (double)ht[2046] / (double)ht[2047]);
 	long long t0 = ht[(2 * 64 + 0) * 8 + 3];     // first QK issue
 	auto T = [&](int role, int j, int ev) { long long x = ht[(role * 64 + j) * 8 + ev]; return x ? (long long)(x - t0) : -1; };
+	if (getenv("GGML_B200_ATTN_SPLIT") && atoi(getenv("GGML_B200_ATTN_SPLIT")) == 5) {
+		// attn_ap_kernel: stream events 0 before s_full wait, 1 scores ready, 2 loaded, 3 max / rescale done, 4 turn granted,
+		// 5 exponentials + pack issued, 6 stores complete; issuing thread per stream: 0 p_full seen, 1 PV issued, 2 QK(u+2) issued
+		long long tz = ht[(0 * 64 + 0) * 8 + 1];
+		auto R = [&](int role, int j, int ev) { long long x = ht[(role * 64 + j) * 8 + ev]; return x ? (long long)(x - tz) : -1; };
+		for (int j = 0; j < nshow; ++j)
+			for (int t = 0; t < 2; ++t) {
+				printf("blk %2d stream %d:", j, t);
+				for (int e = 0; e < 7; ++e) printf(" %7lld", R(t, j, e));
+				printf("   mma:");
+				for (int e = 0; e < 3; ++e) printf(" %7lld", R(2, j, t * 4 + e));
+				printf("\n");
+			}
+	} else {
 	printf("softmax events: 0 wait_s  1 s_ready  2 max_done  3 turn  4 exp_done  5 p_arrived ; mma: 0 pv_wait 1 p_ready 2 pv_issued 3 qk_issued (per tile)\n");
 	for (int j = 0; j < nshow; ++j) {
 		for (int t = 0; t < 2; ++t) {
@@ -63,6 +77,7 @@ int main(int argc, char** argv)
 	}
 	printf("mma warp detail: 0 before k_full wait  1 after  2 elected (QK issue starts)  3 before v_full wait  4 after  5 p_full[a] seen  6 p_full[b] seen\n");
 	for (int j = 1; j < nshow; ++j) { printf("blk %2d mma detail:", j); for (int e = 0; e < 8; ++e) printf(" %7lld", T(3, j, e)); printf("\n"); }
+	}
 	// check a few outputs against a straightforward CPU evaluation (row 0 and row nq-1 of head 0, image 0)
 	std::vector<__half> ho(nQ);
 	CUDA_CHECK(cudaMemcpy(ho.data(), o, nQ * 2, cudaMemcpyDeviceToHost));
