@@ -1104,24 +1104,30 @@ attn_split4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 
-// ------------------------------------------------------------------ heads up to 64 wide: two query tiles in ENFORCED anti-phase
+// ------------------------------------------------------------------ heads up to 64 wide: two query tiles per CTA, scores three blocks deep
 // What bounds the forms above (timelines in profiles/r2_attention_microbench.md, r3_attention.md): a softmax warp alternates between
 // a phase without exponentials (wait for the scores, tcgen05.ld, row maximum, later pack + tcgen05.st + the round trip through the
 // issuing warp and the tensor pipe: PV(j), QK(j+1)) and a phase that is nothing but exponentials. Warps that share a barrier run
-// these phases together, so the MUFU pipe idles during the first and is oversubscribed during the second (45-55 % busy).
+// these phases together, so the MUFU pipe idles during the first and is oversubscribed during the second (45-60 % busy), and a
+// single issuing thread that serves both tiles with predicated K-steps needs ~1500 clk per pair of blocks.
 // Here ONE CTA per SM owns TWO tiles of 128 query rows (streams A, B: warps 0-3 / 4-7, one row per thread) and walks the keys in
 // blocks of 64:
-//   * scores are DOUBLE-BUFFERED per stream (2 x 64 tensor-memory columns): QK(u+2) is issued right behind PV(u), so the scores
-//     of the next block are complete long before a stream asks for them -- the tensor-pipe round trip leaves the critical path;
-//   * the two warps of an SM sub-partition (stream A's and stream B's) hand the MUFU pipe to each other through named barriers:
-//     B starts the exponentials of its block u when A has issued the signal of its block u, A starts block u+1 on B's signal
-//     (p.sig: 1 = signal half-way through the exponentials, 2 = at their end, 0 = free-running). While one stream is in its
-//     exponential phase the other loads, takes the maximum, packs and stores;
+//   * the scores of a stream sit in a ring of THREE buffers (3 x 64 tensor-memory columns): QK(u+3) is issued right behind
+//     PV(u), so a stream finds the scores of the next TWO blocks complete -- the tensor-pipe round trip is off the critical path;
+//   * the softmax loop is SOFTWARE-PIPELINED inside the thread: while the exponentials of block u (MUFU-bound) are in flight, the
+//     same instruction stream loads the scores of block u + 1 and takes their maximum, so a warp has no phase without exponentials
+//     except the store / arrive tail;
+//   * one issuing warp PER STREAM, straight-line issue (compile-time K-steps for d16 = 48 / 64), descriptors precomputed;
 //   * packed f32x2 arithmetic, N_POLY pairs of every 8 pairs as polynomial on the FMA pipe;
-//   * SUMMMA: the row sums come from the tensor core (P x ones, N = 16, into the 16 columns right of the accumulator).
-// Tensor memory: S_A[2] 0..127, S_B[2] 128..255, O_A 256..335, O_B 336..415 (d16 + 16 <= 80 columns each).
-constexpr int AP_KST = 3, AP_VST = 3;
-#ifdef ATTN_AP_TRACE
+//   * SUMMMA (d16 <= 48): the row sums come from the tensor core (P x ones, N = 16, into the 16 columns right of the accumulator).
+// Tensor memory (512 columns): S_A[3] 0..191, S_B[3] 192..383, O_A 384..447, O_B 448..511.
+// mbarrier parity waits only tell consecutive phases apart, and a stream may run ahead of the tensor pipe, so every block waits
+// for PV(u-1) before it hands over P(u): the thread is never more than one completion away from the phase it asks for.
+constexpr int AP_KST = 4, AP_VST = 4, AP_SB = 3;
+#ifndef AP_DBG             // timing experiments (-DAP_DBG=n builds, results wrong): 1 no PV products, 2 no sum products, 4 no QK, 8 no exponentials
+#define AP_DBG 0
+#endif
+#ifdef ATTN_AP_TRACE       // timeline probe build (tools/attn_trace.cu): the clock reads cost ~10 % and stay out of the product
 #define AP_TR(role, j, ev) ATTN_TR(role, j, ev)
 #else
 #define AP_TR(role, j, ev) do { } while (0)
@@ -1137,31 +1143,31 @@ attn_ap_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 	uint8_t* sQ = smem;                              // [2 tiles]
 	uint8_t* sK = sQ + 2 * TB;                       // [AP_KST] tiles of 128 keys
 	uint8_t* sV = sK + AP_KST * TB;                  // [AP_VST]
-	uint8_t* sOnes = sV + AP_VST * TB;               // 16 key rows of 128 B, every f16 = 1.0
+	uint8_t* sOnes = sV + AP_VST * TB;               // 16 key rows of 128 B, every f16 = 1.0 (any swizzle of it is itself)
 	uint64_t* bars = (uint64_t*)(sOnes + 2048);
 	uint64_t* q_full = bars;                         // [2]
 	uint64_t* k_full = q_full + 2;                   // [AP_KST]
 	uint64_t* k_empty = k_full + AP_KST;
 	uint64_t* v_full = k_empty + AP_KST;             // [AP_VST]
 	uint64_t* v_empty = v_full + AP_VST;
-	uint64_t* s_full = v_empty + AP_VST;             // [2 streams][2 buffers]  QK done
-	uint64_t* p_full = s_full + 4;                   // [2][2]  probabilities written (128 arrivals)
-	uint64_t* pv_full = p_full + 4;                  // [2]     PV product of a block done
+	uint64_t* s_full = v_empty + AP_VST;             // [2 streams][3 buffers]  QK done
+	uint64_t* p_full = s_full + 2 * AP_SB;           // [2][3]  probabilities written (128 arrivals)
+	uint64_t* pv_full = p_full + 2 * AP_SB;          // [2]     PV product of a block done
 	uint32_t* tmem_slot = (uint32_t*)(pv_full + 2);
 
 	const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
 	const int q0 = blockIdx.x * (2 * AQ), h = blockIdx.y, b = blockIdx.z;
-	constexpr uint32_t O_BASE = 256, O_STRIDE = 80;
-	constexpr int W_TMA = 8, W_MMA = 9;
-	constexpr int BAR_A2B = 2, BAR_B2A = 6;          // named barriers 2..5 / 6..9: one pair per SM sub-partition
+	constexpr uint32_t S_STRIDE = 64 * AP_SB, O_BASE = 2 * S_STRIDE, O_STRIDE = 64;
+	constexpr int W_TMA = 8, W_MMA = 9;              // warps 9 / 10 issue for stream A / B
 	const int n64 = (p.nk + 63) >> 6;                // key blocks of 64 (>= 3: single-tile contexts run attn_kv1_kernel)
+	const int nfull = p.nk >> 6;                     // a partial block can only be the last one
 
 	if (threadIdx.x == 0) {
 		tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
 		for (int s = 0; s < AP_KST; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 2); }      // freed by both streams
 		for (int s = 0; s < AP_VST; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 2); }
 		for (int t = 0; t < 2; ++t) { mbar_init(&q_full[t], 1); mbar_init(&pv_full[t], 1); }
-		for (int t = 0; t < 4; ++t) { mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 128); }
+		for (int t = 0; t < 2 * AP_SB; ++t) { mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 128); }
 		fence_barrier_init();
 	}
 	if (SUMMMA) {
@@ -1193,12 +1199,12 @@ attn_ap_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 			load_k(0);
 			mbar_expect_tx(&q_full[1], TB);
 			tma_load_4d(sQ + TB, &tmQ, &q_full[1], 0, q0 + AQ, h, b);
-			// K runs one tile ahead of V: QK(u+2) is issued together with PV(u)
-			for (int j = 0; j < p.nblk; ++j) { if (j + 1 < p.nblk) load_k(j + 1); load_v(j); }
+			load_k(1);                                // nblk >= 2
+			// K runs two tiles ahead of V: QK(u+3) is issued together with PV(u)
+			for (int j = 0; j < p.nblk; ++j) { load_v(j); if (j + 2 < p.nblk) load_k(j + 2); }
 		}
 	} else if (warp >= W_MMA) {
-		// ===== one issuing warp PER STREAM (a single issuing thread for both was the bottleneck: ~1500 clk per pair of blocks,
-		// profiles/r3_attention.md). Straight-line issue for full blocks: K-steps are compile-time (NK16), descriptors precomputed.
+		// ===== one issuing warp per stream; straight-line issue for full blocks =====
 		const int t = warp - W_MMA;
 		const int nk16 = NK16 ? NK16 : (p.d16 >> 4);
 		const uint32_t idesc_qk = make_idesc_f16(AQ, 64, 0, 0);
@@ -1209,92 +1215,86 @@ attn_ap_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 		const uint64_t kdesc0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
 		const uint64_t vdesc0 = make_smem_desc_sw128(smem_u32(sV), CHUNK_BYTES, 1024);
 		const uint64_t odesc = make_smem_desc_sw128(smem_u32(sOnes), CHUNK_BYTES, 1024);
-		const uint32_t t_s = tmem_base + (uint32_t)(t * 128), t_o = tmem_base + O_BASE + (uint32_t)t * O_STRIDE;
-		// S_t[u & 1] = Q_t K[64 u .. 64 u + 64)^T : K tile u >> 1 in ring slot ks, rows 64 (u & 1).. (+8 KB = +512 in 16-byte units)
-		auto qk = [&](int u, int ks) {
-			const uint64_t bd = kdesc0 + (uint64_t)(ks * tile16) + (uint64_t)((u & 1) * 512);
-			const uint32_t td = t_s + (uint32_t)((u & 1) * 64);
-			#pragma unroll
-			for (int kk = 0; kk < 4; ++kk)
-				if (kk < nk16) umma_f16(td, qdesc + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc_qk, kk ? 1u : 0u);
-			umma_commit(&s_full[t * 2 + (u & 1)]);
-			if ((u & 1) || u == n64 - 1) umma_commit(&k_empty[ks]);          // this stream is done with the K tile (2 arrivals free it)
-		};
-		// O_t += P_t(u) V[64 u ..): P = 32 packed columns over the start of S_t[u & 1]; 16 keys = 8 columns of P, 16 rows of V
-		auto pv = [&](int u, int vs, auto full_tag) {
-			constexpr bool FULL = decltype(full_tag)::value;
-			const int nkk = FULL ? 4 : ((min(64, p.nk - u * 64) + 15) >> 4);
-			const uint64_t bd = vdesc0 + (uint64_t)(vs * tile16) + (uint64_t)((u & 1) * 512);
-			const uint32_t ta = t_s + (uint32_t)((u & 1) * 64);
-			const uint32_t acc = u ? 1u : 0u;
-			#pragma unroll
-			for (int kk = 0; kk < 4; ++kk)
-				if (FULL || kk < nkk) umma_f16_ts(t_o, ta + kk * 8, bd + (uint64_t)(kk * 128), idesc_pv, kk ? 1u : acc);
-			if (SUMMMA) {
+		const uint32_t t_s = tmem_base + (uint32_t)t * S_STRIDE, t_o = tmem_base + O_BASE + (uint32_t)t * O_STRIDE;
+		int k_waited = -1, v_waited = -1;             // highest K / V tile seen resident
+		// S_t[sb] = Q_t K[64 u .. 64 u + 64)^T : K tile u >> 1, rows 64 (u & 1).. (+8 KB = +512 in 16-byte units)
+		auto qk = [&](int u, int sb) {
+			const int j = u >> 1, ks = j % AP_KST;
+			if (j > k_waited) { mbar_wait(&k_full[ks], (uint32_t)(j / AP_KST) & 1); k_waited = j; tc_fence_after(); }
+			if (elect_one()) {
+				const uint64_t bd = kdesc0 + (uint64_t)(ks * tile16) + (uint64_t)((u & 1) * 512);
+				const uint32_t td = t_s + (uint32_t)(sb * 64);
+				if (!(AP_DBG & 4) || u < 3) {
 				#pragma unroll
 				for (int kk = 0; kk < 4; ++kk)
-					if (FULL || kk < nkk) umma_f16_ts(t_o + p.d16, ta + kk * 8, odesc, idesc_sum, kk ? 1u : acc);
-			}
-			umma_commit(&pv_full[t]);
-			if ((u & 1) || u == n64 - 1) umma_commit(&v_empty[vs]);
-		};
-		mbar_wait(&q_full[t], 0);
-		mbar_wait(&k_full[0], 0);
-		tc_fence_after();
-		if (elect_one()) { qk(0, 0); qk(1, 0); }
-		__syncwarp();
-		const int nfull = p.nk >> 6;
-		int ks = 1 % AP_KST, vs = 0;                  // ring slots of K tile j + 1 and V tile j (j = u >> 1)
-		uint32_t kph = 0, vph = 0;
-		for (int u = 0; u < n64; ++u) {
-			const bool more = u + 2 < n64;
-			if (!(u & 1)) {
-				mbar_wait(&v_full[vs], vph);
-				if (more) mbar_wait(&k_full[ks], kph);
-			}
-			mbar_wait(&p_full[t * 2 + (u & 1)], (uint32_t)(u >> 1) & 1);
-			tc_fence_after();
-			if (elect_one()) {
-				AP_TR(2, u, t * 4 + 0);
-				if (u < nfull) pv(u, vs, std::true_type{}); else pv(u, vs, std::false_type{});
-				AP_TR(2, u, t * 4 + 1);
-				if (more) qk(u + 2, ks);               // in order behind PV(u): S_t[u & 1] / P_t(u) may be overwritten
-				AP_TR(2, u, t * 4 + 2);
+					if (kk < nk16) umma_f16(td, qdesc + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc_qk, kk ? 1u : 0u);
+				}
+				umma_commit(&s_full[t * AP_SB + sb]);
+				if ((u & 1) || u == n64 - 1) umma_commit(&k_empty[ks]);          // this stream is done with the K tile (2 arrivals free it)
 			}
 			__syncwarp();
-			if (u & 1) {
-				if (++ks == AP_KST) { ks = 0; kph ^= 1; }
-				if (++vs == AP_VST) { vs = 0; vph ^= 1; }
+		};
+		// O_t += P_t(u) V[64 u ..): P = 32 packed columns over the start of S_t[sb]; 16 keys = 8 columns of P, 16 rows of V
+		auto pv = [&](int u, int sb, auto full_tag) {
+			constexpr bool FULL = decltype(full_tag)::value;
+			const int j = u >> 1, vs = j % AP_VST;
+			if (j > v_waited) { mbar_wait(&v_full[vs], (uint32_t)(j / AP_VST) & 1); v_waited = j; tc_fence_after(); }
+			if (elect_one()) {
+				const int nkk = FULL ? 4 : ((min(64, p.nk - u * 64) + 15) >> 4);
+				const uint64_t bd = vdesc0 + (uint64_t)(vs * tile16) + (uint64_t)((u & 1) * 512);
+				const uint32_t ta = t_s + (uint32_t)(sb * 64);
+				const uint32_t acc = u ? 1u : 0u;
+				if (!(AP_DBG & 1) || u < 1) {
+				#pragma unroll
+				for (int kk = 0; kk < 4; ++kk)
+					if (FULL || kk < nkk) umma_f16_ts(t_o, ta + kk * 8, bd + (uint64_t)(kk * 128), idesc_pv, kk ? 1u : acc);
+				}
+				if (SUMMMA && (!(AP_DBG & 2) || u < 1)) {
+					#pragma unroll
+					for (int kk = 0; kk < 4; ++kk)
+						if (FULL || kk < nkk) umma_f16_ts(t_o + p.d16, ta + kk * 8, odesc, idesc_sum, kk ? 1u : acc);
+				}
+				umma_commit(&pv_full[t]);
+				if ((u & 1) || u == n64 - 1) umma_commit(&v_empty[vs]);
 			}
+			__syncwarp();
+		};
+		mbar_wait(&q_full[t], 0);
+		tc_fence_after();
+		qk(0, 0); qk(1, 1); qk(2, 2);                 // n64 >= 3
+		int sb = 0; uint32_t ph = 0;                  // ring buffer and barrier phase of block u
+		for (int u = 0; u < n64; ++u) {
+			if (u + 3 < n64) {                        // K tile of QK(u+3): waited for before the probabilities arrive
+				const int j = (u + 3) >> 1;
+				if (j > k_waited) { mbar_wait(&k_full[j % AP_KST], (uint32_t)(j / AP_KST) & 1); k_waited = j; }
+			}
+			{ const int j = u >> 1; if (j > v_waited) { mbar_wait(&v_full[j % AP_VST], (uint32_t)(j / AP_VST) & 1); v_waited = j; } }
+			mbar_wait(&p_full[t * AP_SB + sb], ph);
+			tc_fence_after();
+			if (lane == 0) AP_TR(2, u, t * 4 + 0);
+			if (u < nfull) pv(u, sb, std::true_type{}); else pv(u, sb, std::false_type{});
+			if (lane == 0) AP_TR(2, u, t * 4 + 1);
+			if (u + 3 < n64) qk(u + 3, sb);           // in order behind PV(u): S_t[sb] / P_t(u) may be overwritten
+			if (lane == 0) AP_TR(2, u, t * 4 + 2);
+			if (++sb == AP_SB) { sb = 0; ph ^= 1; }
 		}
 	} else {
 		// ===== softmax: stream t = warp / 4 (query tile), TMEM lane group = warp % 4; one query row per thread =====
 		const int t = warp >> 2, quarter = warp & 3;
 		const int r = quarter * 32 + lane;
 		const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-		const uint32_t ts0 = tmem_base + lane_off + (uint32_t)t * 128;
+		const uint32_t ts0 = tmem_base + lane_off + (uint32_t)t * S_STRIDE;
 		const uint32_t to = tmem_base + O_BASE + (uint32_t)t * O_STRIDE + lane_off;
 		const float sl2 = p.scale_log2;
-		const int sig = p.sig;
 		float m = -INFINITY, l = 0.f;
 #ifdef ATTN_AP_TRACE
-		const bool tr = p.trace != nullptr && quarter == 0 && lane == 0;      // timeline probe (tools/attn_trace.cu, -DATTN_AP_TRACE builds only)
+		const bool tr = p.trace != nullptr && quarter == 0 && lane == 0;
 #else
 		constexpr bool tr = false;
 #endif
 
-		auto block = [&](int u, auto full_tag) {
+		auto row_max = [&](const uint32_t* va, const uint32_t* vb, int valid, auto full_tag) -> float {
 			constexpr bool FULL = decltype(full_tag)::value;
-			const int valid = FULL ? 64 : p.nk - u * 64;                       // 1..63 in the partial (last) block
-			const uint32_t ts = ts0 + (uint32_t)(u & 1) * 64;
-			if (tr) ATTN_TR(t, u, 0);
-			mbar_wait_parked(&s_full[t * 2 + (u & 1)], (uint32_t)(u >> 1) & 1);
-			tc_fence_after();
-			if (tr) ATTN_TR(t, u, 1);
-			uint32_t va[32], vb[32];
-			tmem_ld32(ts, va); tmem_ld32(ts + 32, vb);
-			tmem_ld_wait();
-			if (tr) ATTN_TR(t, u, 2);
 			float mx4[4] = { -INFINITY, -INFINITY, -INFINITY, -INFINITY };
 			if (FULL) {
 				#pragma unroll
@@ -1315,20 +1315,75 @@ attn_ap_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 					if (32 + i < valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(vb[i]));
 				}
 			}
-			const float m_blk = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sl2;
-			// Lazy rescaling: keep the old maximum while the block maximum exceeds it by < 2^8 (f16 probabilities stay < 2^8 x 1).
-			if (u == 0) m = m_blk;
-			else {
+			return fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sl2;
+		};
+		uint64_t acc0 = 0ull, acc1 = 0ull;
+		// exponentials of 32 scores -> 16 packed columns of probabilities at tensor-memory address tp
+		auto pass = [&](uint32_t* v, uint32_t tp, int c, int valid, uint64_t SL, uint64_t MN, auto full_tag) {
+			constexpr bool FULL = decltype(full_tag)::value;
+			uint32_t packed[16];
+			#pragma unroll
+			for (int i = 0; i < 32; i += 2) {
+				const int pi = i >> 1;
+				const uint64_t x2 = fma2(pk2u(v[i], v[i + 1]), SL, MN);
+				float e0, e1;
+				if (N_POLY > 0 && (((pi & 7) * N_POLY) & 7) < N_POLY) ex2_poly2(x2, e0, e1);
+				else { float x0, x1; unpk2(x2, x0, x1); e0 = ex2_approx(x0); e1 = ex2_approx(x1); }
+				if (!FULL) { if (c * 32 + i >= valid) e0 = 0.f; if (c * 32 + i + 1 >= valid) e1 = 0.f; }
+				if (!SUMMMA) { if (pi & 1) acc1 = add2(acc1, pk2(e0, e1)); else acc0 = add2(acc0, pk2(e0, e1)); }
+				__half2 hh = __floats2half2_rn(e0, e1);
+				packed[pi] = *reinterpret_cast<uint32_t*>(&hh);
+			}
+			tmem_st16(tp, packed);
+		};
+		int sb = 0; uint32_t ph = 0;                  // ring buffer and barrier phase of block u
+		// One iteration: block u sits in (ca, cb) with m already covering it; block u + 1 (if any) is loaded into (na, nb).
+		auto step = [&](int u, uint32_t* ca, uint32_t* cb, uint32_t* na, uint32_t* nb, auto cur_full_tag, auto next_tag) {
+			constexpr bool CUR_FULL = decltype(cur_full_tag)::value;
+			constexpr int NEXT = decltype(next_tag)::value;                // 0 none, 1 full, 2 partial
+			const int valid = CUR_FULL ? 64 : p.nk - u * 64;
+			const uint32_t ts = ts0 + (uint32_t)sb * 64;
+			int sbn = sb + 1; uint32_t phn = ph;
+			if (sbn == AP_SB) { sbn = 0; phn ^= 1; }
+			if (tr) AP_TR(t, u, 0);
+			if (NEXT) {
+				mbar_wait(&s_full[t * AP_SB + sbn], phn);
+				tc_fence_after();
+				const uint32_t tn = ts0 + (uint32_t)sbn * 64;
+				tmem_ld32(tn, na); tmem_ld32(tn + 32, nb);
+			}
+			const uint64_t SL = pk2(sl2, sl2), MN = pk2(-m, -m);
+			if (tr) AP_TR(t, u, 1);
+			const bool do_exp = !(AP_DBG & 8);
+			if (do_exp) pass(ca, ts, 0, valid, SL, MN, cur_full_tag);
+			if (tr) AP_TR(t, u, 2);
+			if (u > 0) mbar_wait(&pv_full[t], (uint32_t)(u - 1) & 1);     // PV(u-1): issued a block ago; keeps the phase count in step
+			float m_blk = 0.f;
+			if (NEXT) {
+				tmem_ld_wait();
+				#pragma unroll
+				for (int i = 0; i < 32; ++i) { asm volatile("" : "+r"(na[i])); asm volatile("" : "+r"(nb[i])); }
+				if (tr) AP_TR(t, u, 3);
+				m_blk = NEXT == 1 ? row_max(na, nb, 64, std::true_type{}) : row_max(na, nb, p.nk - (u + 1) * 64, std::false_type{});
+			}
+			if (do_exp) pass(cb, ts + 16, 1, valid, SL, MN, cur_full_tag);
+			if (tr) AP_TR(t, u, 4);
+			tmem_st_wait();
+			tc_fence_before();
+			if (tr) AP_TR(t, u, 5);
+			mbar_arrive(&p_full[t * AP_SB + sb]);
+			if (NEXT) {
+				// Lazy rescaling: keep the old maximum while the block maximum exceeds it by < 2^8 (f16 probabilities stay < 2^8 x 1).
 				const bool need = m_blk > m + 8.0f;
 				if (__any_sync(0xffffffffu, need)) {
 					const float m_new = need ? m_blk : m;
 					const float corr = ex2_approx(m - m_new);
 					m = m_new;
-					l *= corr;
-					mbar_wait(&pv_full[t], (uint32_t)(u - 1) & 1);       // PV(u-1) has landed; PV(u) cannot be in flight yet
+					if (!SUMMMA) { float a0, a1; unpk2(add2(acc0, acc1), a0, a1); l = (l + a0 + a1) * corr; acc0 = 0ull; acc1 = 0ull; }
+					mbar_wait(&pv_full[t], (uint32_t)u & 1);             // PV(u), issued behind the arrival above
 					tc_fence_after();
 					#pragma unroll
-					for (int c0 = 0; c0 < 80; c0 += 16) {
+					for (int c0 = 0; c0 < 64; c0 += 16) {
 						if (c0 < p.d16 + (SUMMMA ? 16 : 0)) {
 							uint32_t o[16];
 							tmem_ld16(to + c0, o);
@@ -1338,56 +1393,48 @@ attn_ap_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 							tmem_st16(to + c0, o);
 						}
 					}
+					tmem_st_wait();
 				}
 			}
-			if (tr) ATTN_TR(t, u, 3);
-			// my turn on the MUFU pipe
-			if (sig) {
-				if (t == 0) { if (u > 0) named_bar_sync(BAR_B2A + quarter, 64); }
-				else named_bar_sync(BAR_A2B + quarter, 64);
-			}
-			auto signal = [&]() {
-				if (t == 0) named_bar_arrive(BAR_A2B + quarter, 64);
-				else if (u + 1 < n64) named_bar_arrive(BAR_B2A + quarter, 64);
-			};
-			if (tr) ATTN_TR(t, u, 4);
-			const uint64_t SL = pk2(sl2, sl2), MN = pk2(-m, -m);
-			uint64_t acc0 = 0ull, acc1 = 0ull;
-			auto pass = [&](uint32_t* v, int c) {
-				uint32_t packed[16];
-				#pragma unroll
-				for (int i = 0; i < 32; i += 2) {
-					const int pi = i >> 1;
-					const uint64_t x2 = fma2(pk2u(v[i], v[i + 1]), SL, MN);
-					float e0, e1;
-					if (N_POLY > 0 && (((pi & 7) * N_POLY) & 7) < N_POLY) ex2_poly2(x2, e0, e1);
-					else { float x0, x1; unpk2(x2, x0, x1); e0 = ex2_approx(x0); e1 = ex2_approx(x1); }
-					if (!FULL) { if (c * 32 + i >= valid) e0 = 0.f; if (c * 32 + i + 1 >= valid) e1 = 0.f; }
-					if (!SUMMMA) { if (pi & 1) acc1 = add2(acc1, pk2(e0, e1)); else acc0 = add2(acc0, pk2(e0, e1)); }
-					__half2 hh = __floats2half2_rn(e0, e1);
-					packed[pi] = *reinterpret_cast<uint32_t*>(&hh);
-				}
-				tmem_st16(ts + c * 16, packed);
-			};
-			pass(va, 0);
-			if (sig == 1) signal();
-			pass(vb, 1);
-			if (sig == 2) signal();
-			if (!SUMMMA) { float a0, a1; unpk2(add2(acc0, acc1), a0, a1); l += a0 + a1; }
-			if (tr) ATTN_TR(t, u, 5);
-			tmem_st_wait();
-			tc_fence_before();
-			if (tr) ATTN_TR(t, u, 6);
-			mbar_arrive(&p_full[t * 2 + (u & 1)]);
+			sb = sbn; ph = phn;
 		};
-		const int nfull = p.nk >> 6;          // a partial block can only be the last one
-		for (int u = 0; u < nfull; ++u) block(u, std::true_type{});
-		if (nfull < n64) block(nfull, std::false_type{});
+		uint32_t a0r[32], b0r[32], a1r[32], b1r[32];
+		{   // block 0
+			mbar_wait_parked(&s_full[t * AP_SB], 0);
+			tc_fence_after();
+			tmem_ld32(ts0, a0r); tmem_ld32(ts0 + 32, b0r);
+			tmem_ld_wait();
+			m = row_max(a0r, b0r, 64, std::true_type{});          // n64 >= 3: block 0 is full
+		}
+		// blocks 0 .. n64 - 2 have a successor; the successor of block n64 - 2 is the last block (full or partial)
+		const bool last_partial = nfull < n64;
+		int u = 0;
+		for (; u + 2 < n64 - 1; u += 2) {
+			step(u, a0r, b0r, a1r, b1r, std::true_type{}, std::integral_constant<int, 1>{});
+			step(u + 1, a1r, b1r, a0r, b0r, std::true_type{}, std::integral_constant<int, 1>{});
+		}
+		// here u is even and n64 - 1 - u is 1 or 2
+		if (n64 - 1 - u == 2) {
+			step(u, a0r, b0r, a1r, b1r, std::true_type{}, std::integral_constant<int, 1>{});
+			if (last_partial) {
+				step(u + 1, a1r, b1r, a0r, b0r, std::true_type{}, std::integral_constant<int, 2>{});
+				step(u + 2, a0r, b0r, a1r, b1r, std::false_type{}, std::integral_constant<int, 0>{});
+			} else {
+				step(u + 1, a1r, b1r, a0r, b0r, std::true_type{}, std::integral_constant<int, 1>{});
+				step(u + 2, a0r, b0r, a1r, b1r, std::true_type{}, std::integral_constant<int, 0>{});
+			}
+		} else {
+			if (last_partial) {
+				step(u, a0r, b0r, a1r, b1r, std::true_type{}, std::integral_constant<int, 2>{});
+				step(u + 1, a1r, b1r, a0r, b0r, std::false_type{}, std::integral_constant<int, 0>{});
+			} else {
+				step(u, a0r, b0r, a1r, b1r, std::true_type{}, std::integral_constant<int, 1>{});
+				step(u + 1, a1r, b1r, a0r, b0r, std::true_type{}, std::integral_constant<int, 0>{});
+			}
+		}
+		if (!SUMMMA) { float s0, s1; unpk2(add2(acc0, acc1), s0, s1); l += s0 + s1; }
 
-		// epilogue: O / l -> f16 -> global memory
-		// the scores are double-buffered, so this thread may be TWO products ahead of the tensor pipe: a parity wait alone cannot
-		// tell phase n64 - 1 from n64 - 3; PV(n64 - 3) is known complete (QK(n64 - 1) completed behind it), so wait phase by phase
-		mbar_wait(&pv_full[t], (uint32_t)(n64 - 2) & 1);
+		// epilogue: O / l -> f16 -> global memory. PV(n64-2) was waited for by the last block: one completion to go.
 		mbar_wait(&pv_full[t], (uint32_t)(n64 - 1) & 1);
 		tc_fence_after();
 		if (SUMMMA) {
@@ -1430,7 +1477,6 @@ attn_ap_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 	__syncthreads();
 	if (warp == W_MMA) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
-
 
 // ------------------------------------------------------------------ single key block (cross-attention, nk <= 128)
 // The text context of a cross-attention has 77 keys (unet.c:110-145): one key block. With one (pair of) query tile(s)
@@ -1690,7 +1736,9 @@ AttnTC* attn_tc_prepare(const View& o, const View& q, const View& k, const View&
 	// GGML_B200_ATTN_SPLIT: 0 = one row per thread (round-1 dual form), 2 = key halves, two CTAs per SM (default: 837 / 272 / 340 us on
 	// the three shapes of profiles/r2_attention_microbench.md against 841 / 300 / 392 us), 4 = key quarters + double-buffered
 	// scores, one CTA per SM (measured slower: 911 / 301 / 350 us -- kept selectable)
-	{ const char* e = getenv("GGML_B200_ATTN_SPLIT"); p.split = p.dual ? (e ? atoi(e) : 2) : 0; if (p.split && p.split != 4 && p.split != 3 && p.split != 5) p.split = 2; }
+	// 5 = two query tiles per CTA, scores three blocks deep, software-pipelined softmax (attn_ap_kernel): default for heads up to 48
+	// wide (SD1.x level 0: 650 us against 820-840 us); 64-wide heads stay on the key halves (253 / 311 us against 247 / 321 us)
+	{ const char* e = getenv("GGML_B200_ATTN_SPLIT"); p.split = p.dual ? (e ? atoi(e) : (p.d16 <= 48 ? 5 : 2)) : 0; if (p.split && p.split != 4 && p.split != 3 && p.split != 5) p.split = 2; }
 	const int nt = (p.d16 > 128 || (p.dual && p.split != 5)) ? 1 : 2;
 	if (p.dual && p.split != 4 && p.split != 3 && p.split != 5) p.stages = std::min(p.stages, 2);             // two CTAs per SM: <= 113 KB each
 	auto total = [&]() { return tile * (nt + 2 * p.stages) + 1024 + 512; };
@@ -1699,17 +1747,17 @@ AttnTC* attn_tc_prepare(const View& o, const View& q, const View& k, const View&
 	// packed softmax arithmetic of the key-halves form (GGML_B200_ATTN_PK: 0 scalar, 1 packed, 2 packed + row sums on the tensor core)
 	{
 		const char* e = getenv("GGML_B200_ATTN_PK");
-		p.pk = p.split == 2 ? (e ? atoi(e) : 0) : 0;
+		p.pk = p.split == 2 ? (e ? atoi(e) : 1) : 0;     // packed: 276 -> 253 us, 341 -> 305 us on the 64-wide shapes
 		if (p.pk == 2 && p.d16 > 48) p.pk = 1;
 		if (p.pk == 2) a->smem += 2048;
-		if (p.pk) { const char* ep = getenv("GGML_B200_ATTN_POLY"); p.npoly = std::max(0, std::min(4, ep ? atoi(ep) : 2)); }
+		if (p.pk) { const char* ep = getenv("GGML_B200_ATTN_POLY"); p.npoly = std::max(0, std::min(2, ep ? atoi(ep) : 1)); }
 	}
 	p.sig = 0;
 	if (p.split == 5) {          // two query tiles per CTA in enforced anti-phase (attn_ap_kernel)
 		const char* e = getenv("GGML_B200_ATTN_PK"); p.pk = e ? atoi(e) : 2;
 		if (p.pk != 1) p.pk = 2;
-		const char* ep = getenv("GGML_B200_ATTN_POLY"); p.npoly = std::max(0, std::min(3, ep ? atoi(ep) : 2));
-		const char* es = getenv("GGML_B200_ATTN_SIG"); p.sig = es ? atoi(es) : 1;
+		if (p.d16 > 48) p.pk = 1;            // no tensor-memory columns left for the sum product next to a 64-wide accumulator
+		const char* ep = getenv("GGML_B200_ATTN_POLY"); p.npoly = std::max(0, std::min(2, ep ? atoi(ep) : 1));
 		a->smem = (size_t)(2 + AP_KST + AP_VST) * CHUNK_BYTES + 2048 + 1024 + 1024;
 	}
 	a->grid = dim3((unsigned)((p.nq + nt * AQ - 1) / (nt * AQ)), (unsigned)p.H, (unsigned)p.B);
@@ -1759,16 +1807,15 @@ void attn_tc_launch(cudaStream_t s, AttnTC* a)
 			CUDA_CHECK(cudaFuncSetAttribute((attn_split_kernel<NP, false, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024)); \
 			CUDA_CHECK(cudaFuncSetAttribute((attn_split_kernel<NP, true, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024)); \
 			CUDA_CHECK(cudaFuncSetAttribute((attn_split_kernel<NP, false, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-		PK_ATTR(0) PK_ATTR(1) PK_ATTR(2) PK_ATTR(3) PK_ATTR(4)
+		PK_ATTR(0) PK_ATTR(1) PK_ATTR(2)
 		#undef PK_ATTR
 		#define AP_ATTR(NP) \
 			CUDA_CHECK(cudaFuncSetAttribute((attn_ap_kernel<NP, true, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
 			CUDA_CHECK(cudaFuncSetAttribute((attn_ap_kernel<NP, true, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-			CUDA_CHECK(cudaFuncSetAttribute((attn_ap_kernel<NP, true, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
 			CUDA_CHECK(cudaFuncSetAttribute((attn_ap_kernel<NP, false, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
 			CUDA_CHECK(cudaFuncSetAttribute((attn_ap_kernel<NP, false, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
 			CUDA_CHECK(cudaFuncSetAttribute((attn_ap_kernel<NP, false, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-		AP_ATTR(0) AP_ATTR(1) AP_ATTR(2) AP_ATTR(3)
+		AP_ATTR(0) AP_ATTR(1) AP_ATTR(2)
 		#undef AP_ATTR
 		CUDA_CHECK(cudaFuncSetAttribute(attn_kv1_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		CUDA_CHECK(cudaFuncSetAttribute(attn_kv1_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1782,11 +1829,11 @@ void attn_tc_launch(cudaStream_t s, AttnTC* a)
 	}
 	if (a->p.split == 5) {
 		#define AP_K(NP, SM, K16) attn_ap_kernel<NP, SM, K16><<<a->grid, 352, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p)
-		#define AP_SM(NP, SM) do { if (a->p.d16 == 48) AP_K(NP, SM, 3); else if (a->p.d16 == 64) AP_K(NP, SM, 4); else AP_K(NP, SM, 0); } while (0)
-		#define AP_CASE(NP) do { if (a->p.pk == 2) AP_SM(NP, true); else AP_SM(NP, false); } while (0)
-		switch (a->p.npoly) { case 0: AP_CASE(0); break; case 1: AP_CASE(1); break; case 2: AP_CASE(2); break; default: AP_CASE(3); break; }
+		#define AP_CASE(NP) do { \
+			if (a->p.pk == 2) { if (a->p.d16 == 48) AP_K(NP, true, 3); else AP_K(NP, true, 0); } \
+			else { if (a->p.d16 == 48) AP_K(NP, false, 3); else if (a->p.d16 == 64) AP_K(NP, false, 4); else AP_K(NP, false, 0); } } while (0)
+		switch (a->p.npoly) { case 0: AP_CASE(0); break; case 1: AP_CASE(1); break; default: AP_CASE(2); break; }
 		#undef AP_CASE
-		#undef AP_SM
 		#undef AP_K
 		g_stats.kernel_launches++;
 		return;
@@ -1812,7 +1859,7 @@ void attn_tc_launch(cudaStream_t s, AttnTC* a)
 		if (a->p.pk) {
 			#define PK_CASE(NP, ST, PKV) attn_split_kernel<NP, ST, PKV><<<a->grid, 320, a->smem, s>>>(a->tmQ, a->tmK, a->tmV, a->p)
 			#define PK_NP(ST, PKV) switch (a->p.npoly) { case 0: PK_CASE(0, ST, PKV); break; case 1: PK_CASE(1, ST, PKV); break; \
-				case 2: PK_CASE(2, ST, PKV); break; case 3: PK_CASE(3, ST, PKV); break; default: PK_CASE(4, ST, PKV); break; }
+				default: PK_CASE(2, ST, PKV); break; }
 			if (a->p.pk == 2) { PK_NP(false, 2) }
 			else if (stag) { PK_NP(true, 1) }
 			else { PK_NP(false, 1) }

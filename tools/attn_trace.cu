@@ -52,14 +52,15 @@ int main(int argc, char** argv)
 	long long t0 = ht[(2 * 64 + 0) * 8 + 3];     // first QK issue
 	auto T = [&](int role, int j, int ev) { long long x = ht[(role * 64 + j) * 8 + ev]; return x ? (long long)(x - t0) : -1; };
 	if (getenv("GGML_B200_ATTN_SPLIT") && atoi(getenv("GGML_B200_ATTN_SPLIT")) == 5) {
-		// attn_ap_kernel: stream events 0 before s_full wait, 1 scores ready, 2 loaded, 3 max / rescale done, 4 turn granted,
-		// 5 exponentials + pack issued, 6 stores complete; issuing thread per stream: 0 p_full seen, 1 PV issued, 2 QK(u+2) issued
-		long long tz = ht[(0 * 64 + 0) * 8 + 1];
+		// attn_ap_kernel: stream events 0 step start, 1 scores of the next block seen + load issued, 2 first half of the exponentials
+		// issued, 3 next block's scores in registers, 4 second half issued, 5 stores complete; issuing warp of the stream:
+		// 0 p_full seen, 1 PV issued, 2 QK(u+3) issued
+		long long tz = ht[(0 * 64 + 0) * 8 + 0];
 		auto R = [&](int role, int j, int ev) { long long x = ht[(role * 64 + j) * 8 + ev]; return x ? (long long)(x - tz) : -1; };
 		for (int j = 0; j < nshow; ++j)
 			for (int t = 0; t < 2; ++t) {
 				printf("blk %2d stream %d:", j, t);
-				for (int e = 0; e < 7; ++e) printf(" %7lld", R(t, j, e));
+				for (int e = 0; e < 6; ++e) printf(" %7lld", R(t, j, e));
 				printf("   mma:");
 				for (int e = 0; e < 3; ++e) printf(" %7lld", R(2, j, t * 4 + e));
 				printf("\n");
