@@ -47,6 +47,11 @@ struct GemmParams {
 	long long* trace;                  // debug timeline of CTA 0's epilogue (GGML_B200_GEMM_TRACE), null in production
 	uint32_t mul_nct, mul_tw, mul_th;  // reciprocal multipliers of n_ctiles / tiles_w / tiles_h: tile coordinates without integer division
 	int split_k, kbps;                 // split-K (gemm_tc_kernel only): blockIdx.z covers k-blocks [z * kbps, (z + 1) * kbps) and writes f32 partials
+	// GroupNorm statistics of the OUTPUT, accumulated by the epilogue of the persistent kernel (mlblock_nn.c:78: the consumer's
+	// group_norm then needs no pass of its own over the tensor): [images][groups][4] fixed-point 64-bit words, see gn_fix_add
+	unsigned long long* gn_stats; int gn_groups, gn_cpg, gn_ppi;      // gn_ppi: rows of one image inside a tile
+	long long rows_per_image_gn;       // plain GEMM: rows of one image (a multiple of the tile height)
+	int gn_nimg_total;                 // images in the output
 };
 
 // What the reduction pass of a split-K launch needs: the real output and the epilogue that the GEMM kernel skipped.
@@ -61,6 +66,7 @@ struct SplitK {
 static uint32_t fastdiv_mul(uint32_t d) { return d <= 1 ? 0u : (uint32_t)((0x100000000ull + d - 1) / d); }
 __device__ __forceinline__ uint32_t fastdiv(uint32_t n, uint32_t mul) { return mul ? __umulhi(n, mul) : n; }
 
+constexpr int GN_TILE_GROUPS = 40;  // groups a 256-column tile can touch (channels per group >= 8)
 struct GemmTC {
 	CUtensorMap tmA, tmB, tmC, tmR;     // tmC / tmR: output store / residual load maps of the persistent kernel
 	GemmParams p;
@@ -107,6 +113,14 @@ __device__ __forceinline__ float geglu_gate(float x, float xb_half, float g)
 	float th; asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(g * t));
 	const float w = fmaf(x, 0.5f, xb_half) * g;
 	return fmaf(w, th, w);
+}
+
+// fixed-point split of a double (same format as kernels_elem.cu: integer part, fraction * 2^40): integer additions commute,
+// so sums accumulated by atomics do not depend on arrival order
+__device__ __forceinline__ void gn_fix_split(double v, unsigned long long& hi, unsigned long long& lo)
+{
+	const double f = floor(v);
+	hi = (unsigned long long)(long long)f; lo = (unsigned long long)(long long)((v - f) * 1099511627776.0);
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -424,6 +438,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 	uint64_t* acc_empty = acc_full + 2;                // [2]
 	uint64_t* res_full  = acc_empty + 2;               // [1]
 	uint32_t* tmem_slot = (uint32_t*)(res_full + 1);
+	unsigned long long* gn_acc = (unsigned long long*)(tmem_slot + 4);       // [P_EPI_MAX_IMG][GN_TILE_GROUPS][4], only when p.gn_stats
 
 	const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
 	if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[6] = clock64();          // kernel entry
@@ -448,6 +463,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 		fence_barrier_init();
 	}
 	if (warp == 9) { if (TWO_SM) tmem_alloc_2sm(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
+	if (p.gn_stats) for (int i = threadIdx.x; i < P_EPI_MAX_IMG * GN_TILE_GROUPS * 4; i += P_THREADS) gn_acc[i] = 0ull;
 	tc_fence_before();
 	__syncthreads();
 	if (csize > 1) cluster_sync_all();                 // peers' barriers exist before anything is multicast to them
@@ -594,6 +610,26 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 				if (chunk_owner) res_load(cluster, 0);
 			}
 		}
+		// GroupNorm statistics of the output (p.gn_stats): after a tile is staged, warp w sums the squares and values of staging
+		// chunk w column pair by column pair (lane & 15) over the rows of one parity (lane >> 4), per image of the tile, and adds
+		// them in fixed point to shared accumulators [image][group of the tile]; these are flushed to global memory with
+		// integer atomics behind the next tile's first barrier (every thread has added by then).
+		int gn_n0 = 0, gn_img0 = 0; bool gn_pending = false;
+		const int gn_nimg = p.gn_stats ? BM / p.gn_ppi : 0;
+		auto gn_flush = [&]() {
+			if (!gn_pending) return;
+			const int g_first = gn_n0 / p.gn_cpg;
+			for (int e = et; e < gn_nimg * GN_TILE_GROUPS; e += 256) {
+				const int im = e / GN_TILE_GROUPS, gl = e - im * GN_TILE_GROUPS, g = g_first + gl, img = gn_img0 + im;
+				unsigned long long* a = gn_acc + (size_t)e * 4;
+				if (g < p.gn_groups && img < p.gn_nimg_total && (a[0] | a[1] | a[2] | a[3])) {
+					unsigned long long* dst = p.gn_stats + ((size_t)img * p.gn_groups + g) * 4;
+					#pragma unroll
+					for (int k = 0; k < 4; ++k) { if (a[k]) atomicAdd(dst + k, a[k]); a[k] = 0ull; }
+				}
+			}
+			gn_pending = false;
+		};
 		uint32_t lt = 0;
 		for (int tile = cluster; tile < num_ctiles; tile += nclusters, ++lt) {
 			int n0, m0, tw0, th0, ti0; tile_coords(tile, n0, m0, tw0, th0, ti0);
@@ -611,6 +647,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 			// the previous tile's stores must have left the staging tile (with a residual the owners waited before re-filling it)
 			if (!HAS_RES && chunk_owner) { if (p.n_stg == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
 			asm volatile("bar.sync 1, 256;" ::: "memory");
+			if (p.gn_stats) gn_flush();                    // the previous tile's sums: complete behind this barrier
 			if (has_vec && next < num_ctiles && et < n_img_tile * p.BN) {
 				int n1, m1, tw1, th1, ti1; tile_coords(next, n1, m1, tw1, th1, ti1);
 				bias_next = bias_of(et, n1, ti1);          // in flight during the tile
@@ -718,10 +755,41 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 					else tma_store_2d(&tmC, my_chunk, out_col0(n0), m0);
 				}
 				tma_store_commit();
-				if (HAS_RES && next < num_ctiles) { if (p.n_stg == 2) tma_store_wait_read1(); else tma_store_wait_read(); res_load(next, (lt + 1) & (uint32_t)(p.n_stg - 1)); }
+				// with one staging tile the residual of the next tile lands where the statistics pass below still reads: load it afterwards
+				if (HAS_RES && next < num_ctiles && !(p.gn_stats && p.n_stg == 1)) { if (p.n_stg == 2) tma_store_wait_read1(); else tma_store_wait_read(); res_load(next, (lt + 1) & (uint32_t)(p.n_stg - 1)); }
 			}
 			GEMM_TR(5);
+			if (p.gn_stats) {
+				const int img0 = p.conv ? ti0 : (int)(m0 / p.rows_per_image_gn);
+				const bool tile_ok = p.conv ? ti0 < p.gn_nimg_total : m0 < p.M;
+				const int col = warp * STG_CHUNK_COLS + (lane & 15) * 2;          // column pair inside the tile
+				if (tile_ok && warp < n_chunks && n0 + col < p.N) {
+					const uint32_t cbase = smem_u32(my_chunk) , u = (uint32_t)(lane & 15) >> 2, w4 = (uint32_t)(lane & 3) * 4;
+					const int gl = (n0 + col) / p.gn_cpg - n0 / p.gn_cpg;
+					for (int im = 0; im < gn_nimg; ++im) {
+						float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+						for (int rr = im * p.gn_ppi + (lane >> 4); rr < (im + 1) * p.gn_ppi; rr += 2) {
+							uint32_t hv;
+							asm volatile("ld.shared.b32 %0, [%1];" : "=r"(hv) : "r"(cbase + (uint32_t)rr * 64 + ((u ^ ((uint32_t)(rr >> 1) & 3)) << 4) + w4));
+							const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hv));
+							s0 += f.x; q0 = fmaf(f.x, f.x, q0); s1 += f.y; q1 = fmaf(f.y, f.y, q1);
+						}
+						if (img0 + im < p.gn_nimg_total) {
+							unsigned long long h, l;
+							unsigned long long* a = gn_acc + ((size_t)im * GN_TILE_GROUPS + gl) * 4;
+							gn_fix_split((double)s0 + (double)s1, h, l); atomicAdd(a, h); atomicAdd(a + 1, l);
+							gn_fix_split((double)q0 + (double)q1, h, l); atomicAdd(a + 2, h); atomicAdd(a + 3, l);
+						}
+					}
+				}
+				gn_n0 = n0; gn_img0 = img0; gn_pending = tile_ok;
+				if (HAS_RES && p.n_stg == 1) {
+					__syncwarp();                              // the whole warp has read its chunk
+					if (chunk_owner && next < num_ctiles) { tma_store_wait_read(); res_load(next, 0); }
+				}
+			}
 		}
+		if (p.gn_stats) { asm volatile("bar.sync 1, 256;" ::: "memory"); gn_flush(); }
 		if (chunk_owner) tma_store_wait_all();
 	}
 	tc_fence_before();
@@ -970,7 +1038,23 @@ static void finish_setup_persistent(GemmTC* g, const GemmEpilogue& ep, int64_t m
 	// A second staging tile lets the TMA store of tile i drain while tile i+1 is written, but the operand ring needs
 	// ~150 KB in flight to cover the ~2500-cycle loaded L2 latency at 57 B/clk: only take it when 5 stages still fit.
 	p.n_stg = 1;
-	auto fixed_bytes = [&](int n_stg) { return 1024 + n_stg * n_chunks * STG_CHUNK_BYTES + (size_t)P_EPI_MAX_IMG * 256 * 4 + (2 * MAX_STAGES + 5) * 8 + 64; };
+	// GroupNorm statistics of the output in the epilogue: whole tiles inside the tensor (no clipped rows), rows of an image
+	// contiguous inside a tile and even in number, channels per group even (a column pair never straddles two groups)
+	p.gn_stats = nullptr; p.gn_groups = 0; p.gn_cpg = 0; p.gn_ppi = BM; p.rows_per_image_gn = 1; p.gn_nimg_total = 0;
+	if (ep.gn_stats && !ep.geglu && ep.gn_groups > 0 && p.N % ep.gn_groups == 0 && env_on("GGML_B200_GN_EPILOGUE", true)) {
+		const int cpg = p.N / ep.gn_groups;
+		bool ok = cpg >= 8 && cpg % 2 == 0;
+		if (p.conv) ok = ok && p.W % p.bw == 0 && p.H % p.bh == 0 && (p.bw * p.bh) % 2 == 0 && p.bi <= P_EPI_MAX_IMG;
+		else ok = ok && ep.gn_rows_per_image > 0 && ep.gn_rows_per_image % BM == 0 && p.M % ep.gn_rows_per_image == 0;
+		if (ok) {
+			p.gn_stats = ep.gn_stats; p.gn_groups = ep.gn_groups; p.gn_cpg = cpg;
+			p.gn_ppi = p.conv ? p.bw * p.bh : BM;
+			p.rows_per_image_gn = p.conv ? 1 : ep.gn_rows_per_image;
+			p.gn_nimg_total = p.conv ? p.n_img : (int)(p.M / ep.gn_rows_per_image);
+		}
+	}
+	const size_t gn_bytes = p.gn_stats ? (size_t)P_EPI_MAX_IMG * GN_TILE_GROUPS * 4 * 8 : 0;
+	auto fixed_bytes = [&](int n_stg) { return 1024 + n_stg * n_chunks * STG_CHUNK_BYTES + (size_t)P_EPI_MAX_IMG * 256 * 4 + (2 * MAX_STAGES + 5) * 8 + 64 + gn_bytes; };
 	// GEGLU tiles are epilogue-bound when K is short (the gate costs ~10 cycles per column): there the second staging tile
 	// is worth a ring stage
 	const int min_stages_2stg = (ep.geglu && p.num_kb <= 8) ? 4 : 5;
@@ -1155,6 +1239,8 @@ static int max_active_clusters(int csize, int sm_count)
 	cache[csize] = n > 0 ? n : -1;
 	return cache[csize];
 }
+
+bool gemm_tc_gn_fused(const GemmTC* g) { return g && g->persistent && g->p.gn_stats != nullptr; }
 
 void gemm_tc_free(GemmTC* g)
 {

@@ -23,7 +23,7 @@ void k_gemm_simt(cudaStream_t s, const View& c, const View& a, const View& b, bo
 // GroupNorm(+affine)(+SiLU): src/dst [W,H,C,N] with channel stride 1 (channels-last).
 // stats: 2*N*groups doubles, zeroed by the caller before launch.
 void k_groupnorm(cudaStream_t s, const View& dst, const View& src, const float* gamma, const float* beta,
-	int groups, float eps, bool silu, unsigned long long* stats);
+	int groups, float eps, bool silu, unsigned long long* stats, bool stats_ready = false);   // stats_ready: the producer's epilogue filled them
 // stats slot: [N][groups][4] 64-bit words (fixed-point sum / sum of squares, integer atomics: order-independent), zeroed per run
 // LayerNorm(+affine) over dim 0 (stride 1), one warp per row.
 void k_layernorm(cudaStream_t s, const View& dst, const View& src, const float* gamma, const float* beta, float eps);
@@ -64,6 +64,11 @@ struct GemmEpilogue {
 	int64_t      ldr = 0;
 	UnaryOp      act = U_NONE;         // applied after bias/rowvec, before residual
 	bool         geglu = false;        // C[M, N/2]: out[:, 16j+i] = h[:, 32j+i] * gelu(h[:, 32j+16+i]) (weights/bias permuted by k_geglu_rows_prep)
+	// GroupNorm statistics of the output wanted by its consumer (mlblock_nn.c:78): [images][groups][4] fixed-point words, zeroed
+	// before the run. A launch that can accumulate them in its epilogue says so through gemm_tc_gn_fused().
+	unsigned long long* gn_stats = nullptr;
+	int          gn_groups = 0;
+	int64_t      gn_rows_per_image = 0; // rows of C per image (plain GEMM)
 };
 
 struct GemmTC;  // opaque prepared launch (tensor maps etc.)
@@ -74,6 +79,7 @@ GemmTC* gemm_tc_prepare(const __half* A, int64_t lda, const __half* B, int64_t l
 GemmTC* conv3x3_tc_prepare(const __half* x, int64_t n_img, int64_t H, int64_t W, int64_t Cin,
 	const __half* Wt, void* C, DT c_dt, int64_t Cout, const GemmEpilogue& ep, int sm_count);
 void gemm_tc_launch(cudaStream_t s, GemmTC* g);
+bool gemm_tc_gn_fused(const GemmTC* g);   // the launch adds the GroupNorm statistics of its output to ep.gn_stats
 void gemm_tc_free(GemmTC* g);
 bool gemm_tc_supported(int64_t M, int64_t N, int64_t K);
 

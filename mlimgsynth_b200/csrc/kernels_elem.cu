@@ -800,7 +800,7 @@ static GnGeom gn_geom(long long HW, int C, long long N, bool fast)
 
 // stats: [N][groups][4] 64-bit words (fixed-point sums, see gn_fix_add), zeroed before the run
 void k_groupnorm(cudaStream_t s, const View& dst, const View& src, const float* gamma, const float* beta,
-	int groups, float eps, bool silu, unsigned long long* stats)
+	int groups, float eps, bool silu, unsigned long long* stats, bool stats_ready)
 {
 	int C = (int)src.ne[2]; long long W = src.ne[0], H = src.ne[1], N = src.ne[3], HW = W * H;
 	int cpg = (C + groups - 1) / groups;
@@ -811,7 +811,7 @@ void k_groupnorm(cudaStream_t s, const View& dst, const View& src, const float* 
 		// small slices: single pass, one block per (image, group)
 		static const bool small_on = !(getenv("GGML_B200_GN_SMALL") && atoi(getenv("GGML_B200_GN_SMALL")) == 0);
 		const long long slice2 = HW * (cpg / 2);                 // half2 units per (image, group)
-		if (small_on && C == groups * cpg && cpg % 2 == 0 && slice2 <= 256LL * 12 && HW < (1 << 24)) {          // measured: beyond ~12 values per thread the two-kernel path wins
+		if (!stats_ready && small_on && C == groups * cpg && cpg % 2 == 0 && slice2 <= 256LL * 12 && HW < (1 << 24)) {          // measured: beyond ~12 values per thread the two-kernel path wins
 			dim3 grid((unsigned)groups, (unsigned)N);
 			const __half* xp = (const __half*)src.ptr; __half* yp = (__half*)dst.ptr;
 			const int nv = (int)((slice2 + 255) / 256);
@@ -828,16 +828,18 @@ void k_groupnorm(cudaStream_t s, const View& dst, const View& src, const float* 
 		const size_t smem = groups * 2 * sizeof(float);
 		static bool attr = false;
 		if (!attr) { CUDA_CHECK(cudaFuncSetAttribute(gn_stats_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
-		gn_stats_fast_kernel<<<grid, threads, gn_stats_smem(G.planes, slab_chunks, groups), s>>>((const __half*)src.ptr, HW, C, cpg, groups, src.st[3], src.st[0], stats, pix_per_block, slab_chunks, nslabs);
+		if (!stats_ready)
+			gn_stats_fast_kernel<<<grid, threads, gn_stats_smem(G.planes, slab_chunks, groups), s>>>((const __half*)src.ptr, HW, C, cpg, groups, src.st[3], src.st[0], stats, pix_per_block, slab_chunks, nslabs);
 		if (silu)
 			gn_apply_fast_kernel<true><<<grid, threads, smem, s>>>((const __half*)src.ptr, (__half*)dst.ptr, HW, C, cpg, groups, src.st[3], src.st[0],
 				dst.st[3], dst.st[0], gamma, beta, stats, eps, pix_per_block, slab_chunks, nslabs);
 		else
 			gn_apply_fast_kernel<false><<<grid, threads, smem, s>>>((const __half*)src.ptr, (__half*)dst.ptr, HW, C, cpg, groups, src.st[3], src.st[0],
 				dst.st[3], dst.st[0], gamma, beta, stats, eps, pix_per_block, slab_chunks, nslabs);
-		g_stats.kernel_launches += 2;
+		g_stats.kernel_launches += stats_ready ? 1 : 2;
 		return;
 	}
+	if (stats_ready) B200_FATAL("k_groupnorm: epilogue statistics are only consumed by the f16 path");
 	const GnGeom G = gn_geom(HW, C, N, false);
 	const int threads = G.threads, slab_chunks = G.slab_chunks, nslabs = G.nslabs, pix_per_block = G.pix_per_block;
 	dim3 g1(G.grid_x, (unsigned)N);

@@ -56,6 +56,10 @@ struct Step {
 	GemmTC* tc = nullptr;
 	AttnTC* atc = nullptr; bool atc_checked = false;
 	size_t stats_off = 0;               // groupnorm statistics slot in the zero region
+	// GroupNorm statistics accumulated by the producing GEMM / conv epilogue (mlblock_nn.c:78): the producer step carries
+	// gn_groups > 0 and the slot, the consumer the producer's index; whether the launch really does it is known once the
+	// producer is prepared (gemm_tc_gn_fused)
+	int gn_groups = 0; int64_t gn_rows_per_image = 0; int gn_producer = -1;
 	const ggml_tensor* leaf = nullptr;  // weight prep: source leaf (+ version it was prepared at)
 	uint64_t leaf_version = ~0ull;
 	const char* name = "";
@@ -890,12 +894,29 @@ void Builder::plan_node(ggml_tensor* t)
 		}
 		if (t->ne[2] % 8) B200_FATAL("group_norm: channel count %lld must be a multiple of 8", (long long)t->ne[2]);
 		PT o = new_pt_nhwc(DT_F16, t->ne[0], t->ne[1], t->ne[2], t->ne[3]);
+		// the statistics can come from the epilogue of the GEMM / conv that wrote exactly this tensor (last writer of its buffer)
+		int producer = -1;
+		if (!env_flag("GGML_B200_NO_GN_EPILOGUE")) {
+			for (int i = (int)P->steps.size() - 1; i >= 0; --i) {
+				const Step& ps = P->steps[i];
+				if (ps.out.buf != a.buf) continue;
+				bool same = (ps.kind == S_GEMM_TC || ps.kind == S_CONV_TC) && ps.out.dt == DT_F16 && ps.out.off == a.off && ps.out.numel() == a.numel() &&
+					!(ps.kind == S_GEMM_TC && (ps.iparam[0] == 1 || ps.ldc != ps.N)) && ps.N == a.ne[2] && (ps.gn_groups == 0 || ps.gn_groups == groups);
+				if (same) producer = i;
+				break;
+			}
+		}
 		Step& s = emit(S_GROUPNORM, "groupnorm");
 		s.out = o; s.in[0] = a; s.n_in = 1; s.fparam = eps; s.iparam[0] = groups; s.iparam[1] = silu ? 1 : 0;
 		if (has_w) { s.bias = gw; s.has_bias = true; }
 		if (has_b) { s.rowvec = gb; s.has_rowvec = true; }
-		s.stats_off = P->zero_bytes;
-		P->zero_bytes += (size_t)4 * groups * t->ne[3] * sizeof(unsigned long long);     // fixed-point (hi, lo) sum and sum of squares
+		if (producer >= 0 && P->steps[producer].gn_groups == groups) s.stats_off = P->steps[producer].stats_off;      // a second consumer of the same statistics
+		else {
+			s.stats_off = P->zero_bytes;
+			P->zero_bytes += (size_t)4 * groups * t->ne[3] * sizeof(unsigned long long);     // fixed-point (hi, lo) sum and sum of squares
+			if (producer >= 0) { Step& ps = P->steps[producer]; ps.gn_groups = groups; ps.stats_off = s.stats_off; ps.gn_rows_per_image = a.ne[0] * a.ne[1]; }
+		}
+		s.gn_producer = producer;
 		done[t] = true;
 		finish(last, o);
 	} break;
@@ -1124,7 +1145,8 @@ static void run_step(Plan* P, Step& s, cudaStream_t st)
 		k_groupnorm(st, view_of(P, s.out), view_of(P, s.in[0]),
 			s.has_bias ? (const float*)buf_ptr(P, s.bias) : nullptr, s.has_rowvec ? (const float*)buf_ptr(P, s.rowvec) : nullptr,
 			s.iparam[0], s.fparam, s.iparam[1] != 0,
-			(unsigned long long*)((char*)P->arena + P->bufs[P->zero_buf].off + s.stats_off));
+			(unsigned long long*)((char*)P->arena + P->bufs[P->zero_buf].off + s.stats_off),
+			s.gn_producer >= 0 && gemm_tc_gn_fused(P->steps[s.gn_producer].tc));
 		break;
 	case S_LAYERNORM:
 		k_layernorm(st, view_of(P, s.out), view_of(P, s.in[0]),
@@ -1156,6 +1178,10 @@ static void run_step(Plan* P, Step& s, cudaStream_t st)
 			if (s.has_residual) { ep.residual = buf_ptr(P, s.residual); ep.residual_dt = s.residual.dt; ep.ldr = s.ldc; }
 			ep.act = s.act;
 			ep.geglu = s.kind == S_GEMM_TC && s.iparam[0] == 1;
+			if (s.gn_groups > 0) {
+				ep.gn_stats = (unsigned long long*)((char*)P->arena + P->bufs[P->zero_buf].off + s.stats_off);
+				ep.gn_groups = s.gn_groups; ep.gn_rows_per_image = s.gn_rows_per_image;
+			}
 			if (s.kind == S_GEMM_TC)
 				s.tc = gemm_tc_prepare((const __half*)buf_ptr(P, s.in[0]), s.lda, (const __half*)buf_ptr(P, s.in[1]), s.ldb,
 					buf_ptr(P, s.out), s.out.dt, s.ldc, s.M, s.N, s.K, ep, P->be->sm_count);
@@ -1181,6 +1207,7 @@ static void dump_plan(Plan* P)
 	for (Step& s : P->steps) hist[kn[s.kind]]++;
 	g_last_plan_hist = hist; g_last_plan_hist["steps"] = (int)P->steps.size(); g_last_plan_hist["preps"] = (int)P->prep.size();
 	for (Step& s : P->steps) g_last_plan_hist[std::string("name:") + s.name]++;
+	for (Step& s : P->steps) if (s.kind == S_GROUPNORM && s.gn_producer >= 0) g_last_plan_hist["gn_from_epilogue"]++;    // planned; the producer's tile mode decides
 	std::string line;
 	for (auto& kv : hist) line += kv.first + ":" + std::to_string(kv.second) + " ";
 	if (env_flag("GGML_B200_QUIET")) return;      // (the histogram above is always recorded)

@@ -304,3 +304,47 @@ def test_embedding_projection_fusion_matches_unfused(ref, eng, monkeypatch):
     (_,), (plain,) = run_both(build, ref, eng, 5)
     assert max_rel_err(fused, r) <= BLOCK_TOL and max_rel_err(plain, r) <= BLOCK_TOL
     assert max_rel_err(fused, plain) <= OP_TOL
+
+
+# ---------------------------------------------------------------- GroupNorm statistics from the producer's epilogue
+# The persistent GEMM / conv kernel accumulates the per-(image, group) sums of its own output while the tile is staged for the
+# TMA store; the group_norm that follows (mlblock_nn.c:78) then only applies. Checked against the oracle, against the
+# two-pass path (GGML_B200_NO_GN_EPILOGUE=1), and by the launch count that the statistics kernel really disappeared.
+@pytest.mark.parametrize("W,H,Cin,Cout,k,N,fused_launches", [
+    (64, 64, 320, 320, 3, 2, 1), (32, 32, 640, 640, 3, 2, 1), (16, 16, 640, 1280, 3, 4, 1),
+    (8, 8, 1280, 1280, 3, 4, 0),          # few tiles, long K: the split-K kernel runs, the statistics stay with the group_norm
+    (32, 32, 320, 640, 1, 2, 1), (64, 64, 128, 256, 3, 1, 1), (16, 16, 256, 512, 1, 3, 1), (64, 32, 96, 320, 3, 3, 1),
+    (8, 8, 320, 1280, 3, 4, 1),           # two images per 128-row tile
+])
+def test_groupnorm_stats_from_epilogue(ref, eng, W, H, Cin, Cout, k, N, fused_launches, monkeypatch):
+    def build(b):
+        x = b.conv2d(b.inp(N, Cin, H, W), Cout, k, 1, k // 2)
+        return b.g.ggml_silu_inplace(b.cc, b.groupnorm32(x))
+    l0 = eng.stats()["kernel_launches"]
+    (r,), (fused,) = run_both(build, ref, eng, 7)
+    l1 = eng.stats()["kernel_launches"]
+    monkeypatch.setenv("GGML_B200_NO_GN_EPILOGUE", "1")
+    (_,), (plain,) = run_both(build, ref, eng, 7)
+    l2 = eng.stats()["kernel_launches"]
+    assert max_rel_err(fused, r) <= OP_TOL and max_rel_err(plain, r) <= OP_TOL
+    assert max_rel_err(fused, plain) <= 1e-3
+    assert (l2 - l1) - (l1 - l0) == fused_launches, "statistics pass: %d vs %d launches" % (l1 - l0, l2 - l1)
+
+
+def test_groupnorm_stats_from_epilogue_blocks(ref, eng, monkeypatch):
+    """Residual and time-embedding epilogues as producers (resnet -> resnet -> transformer GroupNorm), both tile modes."""
+    def build(b):
+        emb = b.inp(2, 1280)
+        h = b.conv2d(b.inp(2, 4, 32, 32), 320)
+        h = b.resnet(h, emb, 320)
+        h = b.resnet(h, emb, 640)
+        return b.g.ggml_silu_inplace(b.cc, b.groupnorm32(h))
+    (r,), (fused,) = run_both(build, ref, eng, 8)
+    monkeypatch.setenv("GGML_B200_GEMM_FORCE", "160,1,1,1")
+    (_,), (pair,) = run_both(build, ref, eng, 8)
+    monkeypatch.delenv("GGML_B200_GEMM_FORCE")
+    monkeypatch.setenv("GGML_B200_NO_GN_EPILOGUE", "1")
+    (_,), (plain,) = run_both(build, ref, eng, 8)
+    for x in (fused, pair, plain):
+        assert max_rel_err(x, r) <= BLOCK_TOL
+    assert max_rel_err(fused, plain) <= 2e-3 and max_rel_err(pair, plain) <= 2e-3

@@ -17,7 +17,7 @@ lib.ggml_b200_last_plan_count.argtypes = [ctypes.c_char_p]
 def plan(build):
     G = blocks.Graph(eng); o = build(blocks.B(G, 0)); G.run(o)
     keys = ["steps", "GEMM_TC", "CONV_TC", "ATTENTION", "GROUPNORM", "LAYERNORM", "GEGLU", "COPY", "UNARY", "BINARY", "GEMM_SIMT",
-            "name:linear_fused", "name:linear_geglu", "name:concat_a"]
+            "name:linear_fused", "name:linear_geglu", "name:concat_a", "gn_from_epilogue"]
     r = {k: lib.ggml_b200_last_plan_count(k.encode()) for k in keys}
     G.free()
     return r
@@ -79,3 +79,13 @@ def test_transformer_block_fusions(fused):
 def test_feed_forward_is_two_gemms(fused):
     r = fused["ff"]
     assert r["GEMM_TC"] == 2 and r["name:linear_geglu"] == 1 and r["BINARY"] == 0
+
+
+def test_groupnorm_statistics_come_from_the_producer(fused):
+    """Every group_norm whose input was written by a tensor-core GEMM / conv asks that launch for its statistics
+    (mlblock_nn.c:78): conv_in -> GN1, conv1 -> GN2 and resnet -> next GN1; the switch undoes it."""
+    assert fused["resnet"]["gn_from_epilogue"] == 2
+    assert fused["resnets"]["gn_from_epilogue"] == 6
+    assert fused["transformer"]["gn_from_epilogue"] == 1
+    plain = run({"GGML_B200_NO_GN_EPILOGUE": "1"})
+    assert plain["resnets"]["gn_from_epilogue"] == 0 and plain["resnets"]["GROUPNORM"] == fused["resnets"]["GROUPNORM"]
