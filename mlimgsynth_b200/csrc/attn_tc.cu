@@ -35,7 +35,7 @@ constexpr int A_TMEM_COLS = 512;
 constexpr int A_MAX_STAGES = 4;
 
 struct AttnParams {
-	int d, d16, dchunks, nq, nk, H, B, stages, nblk, pingpong, sep_p, dual, npoly, split, park, pk, sig;
+	int d, d16, dchunks, nq, nk, H, B, stages, nblk, pingpong, sep_p, dual, npoly, split, park, pk;
 	float scale_log2;
 	void* o; long long so_t, so_h, so_b;
 	long long* trace;     // debug timeline (tools/attn_trace.cu); null in production
@@ -1752,8 +1752,7 @@ AttnTC* attn_tc_prepare(const View& o, const View& q, const View& k, const View&
 		if (p.pk == 2) a->smem += 2048;
 		if (p.pk) { const char* ep = getenv("GGML_B200_ATTN_POLY"); p.npoly = std::max(0, std::min(2, ep ? atoi(ep) : 1)); }
 	}
-	p.sig = 0;
-	if (p.split == 5) {          // two query tiles per CTA in enforced anti-phase (attn_ap_kernel)
+	if (p.split == 5) {          // two query tiles per CTA, scores three blocks deep (attn_ap_kernel)
 		const char* e = getenv("GGML_B200_ATTN_PK"); p.pk = e ? atoi(e) : 2;
 		if (p.pk != 1) p.pk = 2;
 		if (p.d16 > 48) p.pk = 1;            // no tensor-memory columns left for the sum product next to a 64-wide accumulator

@@ -117,10 +117,12 @@ __device__ __forceinline__ float geglu_gate(float x, float xb_half, float g)
 
 // fixed-point split of a double (same format as kernels_elem.cu: integer part, fraction * 2^40): integer additions commute,
 // so sums accumulated by atomics do not depend on arrival order
-__device__ __forceinline__ void gn_fix_split(double v, unsigned long long& hi, unsigned long long& lo)
+// A tile's share of a group sum is a few thousand f16 values: f32 holds it to 1e-7 relative, and the split of an f32 is exact
+// (the fraction of an f32 times 2^40 is an integer). No FP64 and no 64-bit float conversions in the epilogue.
+__device__ __forceinline__ void gn_fix_split(float v, unsigned long long& hi, unsigned long long& lo)
 {
-	const double f = floor(v);
-	hi = (unsigned long long)(long long)f; lo = (unsigned long long)(long long)((v - f) * 1099511627776.0);
+	const float f = floorf(v);
+	hi = (unsigned long long)(long long)f; lo = (unsigned long long)(long long)((v - f) * 1099511627776.0f);
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -420,7 +422,10 @@ __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile
 __device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_count_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
 
-template <int ACT, bool HAS_RES, bool TWO_SM>     // TWO_SM: tcgen05 cta_group::2 CTA pair (needs a cluster launch); ACT: 0 none, 1 SiLU, 2 run-time p.act, 3 GEGLU gate; HAS_RES: f16 residual tile added in the epilogue
+// TWO_SM: tcgen05 cta_group::2 CTA pair (needs a cluster launch); ACT: 0 none, 1 SiLU, 2 run-time p.act, 3 GEGLU gate; HAS_RES: f16
+// residual tile added in the epilogue; GNS: GroupNorm statistics of the output (p.gn_stats) -- compile time, so that the launches
+// without a group_norm behind them keep the lean epilogue (the run-time form cost them 30 registers and 1-8 %)
+template <int ACT, bool HAS_RES, bool TWO_SM, bool GNS = false>
 __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
 	const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmParams p)
@@ -438,7 +443,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 	uint64_t* acc_empty = acc_full + 2;                // [2]
 	uint64_t* res_full  = acc_empty + 2;               // [1]
 	uint32_t* tmem_slot = (uint32_t*)(res_full + 1);
-	unsigned long long* gn_acc = (unsigned long long*)(tmem_slot + 4);       // [P_EPI_MAX_IMG][GN_TILE_GROUPS][4], only when p.gn_stats
+	float2* gn_part = (float2*)(tmem_slot + 4);        // GNS: [images of a tile][256 epilogue threads] (sum, sum of squares) of a column pair
 
 	const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
 	if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[6] = clock64();          // kernel entry
@@ -463,7 +468,6 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 		fence_barrier_init();
 	}
 	if (warp == 9) { if (TWO_SM) tmem_alloc_2sm(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
-	if (p.gn_stats) for (int i = threadIdx.x; i < P_EPI_MAX_IMG * GN_TILE_GROUPS * 4; i += P_THREADS) gn_acc[i] = 0ull;
 	tc_fence_before();
 	__syncthreads();
 	if (csize > 1) cluster_sync_all();                 // peers' barriers exist before anything is multicast to them
@@ -610,23 +614,30 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 				if (chunk_owner) res_load(cluster, 0);
 			}
 		}
-		// GroupNorm statistics of the output (p.gn_stats): after a tile is staged, warp w sums the squares and values of staging
-		// chunk w column pair by column pair (lane & 15) over the rows of one parity (lane >> 4), per image of the tile, and adds
-		// them in fixed point to shared accumulators [image][group of the tile]; these are flushed to global memory with
-		// integer atomics behind the next tile's first barrier (every thread has added by then).
+		// GroupNorm statistics of the output (GNS): after a tile is staged, warp w sums the values and squares of staging chunk w,
+		// one column pair per lane (lane & 15) over the rows of one parity (lane >> 4), per image of the tile, and leaves them in
+		// shared memory. Behind the next tile's first barrier one thread per (image, group) adds up the pairs of its group in a
+		// fixed order and sends the sums to global memory as fixed-point integer atomics: bit-reproducible, and no
+		// shared-memory atomics (64-bit ones are CAS loops: 30 us per launch when 40 lanes meet on one word).
 		int gn_n0 = 0, gn_img0 = 0; bool gn_pending = false;
-		const int gn_nimg = p.gn_stats ? BM / p.gn_ppi : 0;
+		const int gn_nimg = GNS ? BM / p.gn_ppi : 0;
 		auto gn_flush = [&]() {
 			if (!gn_pending) return;
-			const int g_first = gn_n0 / p.gn_cpg;
+			const int g_first = gn_n0 / p.gn_cpg, c_end = min(p.BN, p.N - gn_n0);
 			for (int e = et; e < gn_nimg * GN_TILE_GROUPS; e += 256) {
 				const int im = e / GN_TILE_GROUPS, gl = e - im * GN_TILE_GROUPS, g = g_first + gl, img = gn_img0 + im;
-				unsigned long long* a = gn_acc + (size_t)e * 4;
-				if (g < p.gn_groups && img < p.gn_nimg_total && (a[0] | a[1] | a[2] | a[3])) {
-					unsigned long long* dst = p.gn_stats + ((size_t)img * p.gn_groups + g) * 4;
-					#pragma unroll
-					for (int k = 0; k < 4; ++k) { if (a[k]) atomicAdd(dst + k, a[k]); a[k] = 0ull; }
+				const int c_lo = max(g * p.gn_cpg - gn_n0, 0), c_hi = min((g + 1) * p.gn_cpg - gn_n0, c_end);
+				if (g >= p.gn_groups || img >= p.gn_nimg_total || c_lo >= c_hi) continue;
+				float a = 0.f, b = 0.f;
+				for (int c = c_lo; c < c_hi; c += 2) {
+					const int t0 = (c >> 5) * 32 + ((c & 31) >> 1);            // thread that summed this pair's even rows; +16: odd rows
+					const float2 x = gn_part[im * 256 + t0], y = gn_part[im * 256 + t0 + 16];
+					a += x.x + y.x; b += x.y + y.y;
 				}
+				unsigned long long* dst = p.gn_stats + ((size_t)img * p.gn_groups + g) * 4;
+				unsigned long long h, l;
+				gn_fix_split(a, h, l); atomicAdd(dst, h); atomicAdd(dst + 1, l);
+				gn_fix_split(b, h, l); atomicAdd(dst + 2, h); atomicAdd(dst + 3, l);
 			}
 			gn_pending = false;
 		};
@@ -647,7 +658,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 			// the previous tile's stores must have left the staging tile (with a residual the owners waited before re-filling it)
 			if (!HAS_RES && chunk_owner) { if (p.n_stg == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
 			asm volatile("bar.sync 1, 256;" ::: "memory");
-			if (p.gn_stats) gn_flush();                    // the previous tile's sums: complete behind this barrier
+			if (GNS) gn_flush();                           // the previous tile's sums: complete behind this barrier
 			if (has_vec && next < num_ctiles && et < n_img_tile * p.BN) {
 				int n1, m1, tw1, th1, ti1; tile_coords(next, n1, m1, tw1, th1, ti1);
 				bias_next = bias_of(et, n1, ti1);          // in flight during the tile
@@ -756,30 +767,25 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 				}
 				tma_store_commit();
 				// with one staging tile the residual of the next tile lands where the statistics pass below still reads: load it afterwards
-				if (HAS_RES && next < num_ctiles && !(p.gn_stats && p.n_stg == 1)) { if (p.n_stg == 2) tma_store_wait_read1(); else tma_store_wait_read(); res_load(next, (lt + 1) & (uint32_t)(p.n_stg - 1)); }
+				if (HAS_RES && next < num_ctiles && !(GNS && p.n_stg == 1)) { if (p.n_stg == 2) tma_store_wait_read1(); else tma_store_wait_read(); res_load(next, (lt + 1) & (uint32_t)(p.n_stg - 1)); }
 			}
 			GEMM_TR(5);
-			if (p.gn_stats) {
+			if (GNS) {
 				const int img0 = p.conv ? ti0 : (int)(m0 / p.rows_per_image_gn);
 				const bool tile_ok = p.conv ? ti0 < p.gn_nimg_total : m0 < p.M;
 				const int col = warp * STG_CHUNK_COLS + (lane & 15) * 2;          // column pair inside the tile
 				if (tile_ok && warp < n_chunks && n0 + col < p.N) {
-					const uint32_t cbase = smem_u32(my_chunk) , u = (uint32_t)(lane & 15) >> 2, w4 = (uint32_t)(lane & 3) * 4;
-					const int gl = (n0 + col) / p.gn_cpg - n0 / p.gn_cpg;
+					const uint32_t cbase = smem_u32(my_chunk), u = (uint32_t)(lane & 15) >> 2, w4 = (uint32_t)(lane & 3) * 4;
 					for (int im = 0; im < gn_nimg; ++im) {
 						float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+						#pragma unroll 8
 						for (int rr = im * p.gn_ppi + (lane >> 4); rr < (im + 1) * p.gn_ppi; rr += 2) {
 							uint32_t hv;
 							asm volatile("ld.shared.b32 %0, [%1];" : "=r"(hv) : "r"(cbase + (uint32_t)rr * 64 + ((u ^ ((uint32_t)(rr >> 1) & 3)) << 4) + w4));
 							const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hv));
 							s0 += f.x; q0 = fmaf(f.x, f.x, q0); s1 += f.y; q1 = fmaf(f.y, f.y, q1);
 						}
-						if (img0 + im < p.gn_nimg_total) {
-							unsigned long long h, l;
-							unsigned long long* a = gn_acc + ((size_t)im * GN_TILE_GROUPS + gl) * 4;
-							gn_fix_split((double)s0 + (double)s1, h, l); atomicAdd(a, h); atomicAdd(a + 1, l);
-							gn_fix_split((double)q0 + (double)q1, h, l); atomicAdd(a + 2, h); atomicAdd(a + 3, l);
-						}
+						gn_part[im * 256 + et] = make_float2(s0 + s1, q0 + q1);
 					}
 				}
 				gn_n0 = n0; gn_img0 = img0; gn_pending = tile_ok;
@@ -789,7 +795,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 				}
 			}
 		}
-		if (p.gn_stats) { asm volatile("bar.sync 1, 256;" ::: "memory"); gn_flush(); }
+		if (GNS) { asm volatile("bar.sync 1, 256;" ::: "memory"); gn_flush(); }
 		if (chunk_owner) tma_store_wait_all();
 	}
 	tc_fence_before();
@@ -1053,7 +1059,7 @@ static void finish_setup_persistent(GemmTC* g, const GemmEpilogue& ep, int64_t m
 			p.gn_nimg_total = p.conv ? p.n_img : (int)(p.M / ep.gn_rows_per_image);
 		}
 	}
-	const size_t gn_bytes = p.gn_stats ? (size_t)P_EPI_MAX_IMG * GN_TILE_GROUPS * 4 * 8 : 0;
+	const size_t gn_bytes = p.gn_stats ? (size_t)(BM / p.gn_ppi) * 256 * sizeof(float2) : 0;
 	auto fixed_bytes = [&](int n_stg) { return 1024 + n_stg * n_chunks * STG_CHUNK_BYTES + (size_t)P_EPI_MAX_IMG * 256 * 4 + (2 * MAX_STAGES + 5) * 8 + 64 + gn_bytes; };
 	// GEGLU tiles are epilogue-bound when K is short (the gate costs ~10 cycles per column): there the second staging tile
 	// is worth a ring stage
@@ -1168,6 +1174,14 @@ template <bool TWO_SM> static PersistentKernel persistent_variant_t(const GemmPa
 	const int act = p.act == U_NONE ? 0 : p.act == U_SILU ? 1 : 2;
 	const bool res = p.residual != nullptr;
 	if (p.geglu) return gemm_tc_persistent_kernel<3, false, TWO_SM>;
+	if (p.gn_stats) switch (act * 2 + (res ? 1 : 0)) {
+	case 0: return gemm_tc_persistent_kernel<0, false, TWO_SM, true>;
+	case 1: return gemm_tc_persistent_kernel<0, true, TWO_SM, true>;
+	case 2: return gemm_tc_persistent_kernel<1, false, TWO_SM, true>;
+	case 3: return gemm_tc_persistent_kernel<1, true, TWO_SM, true>;
+	case 4: return gemm_tc_persistent_kernel<2, false, TWO_SM, true>;
+	default: return gemm_tc_persistent_kernel<2, true, TWO_SM, true>;
+	}
 	switch (act * 2 + (res ? 1 : 0)) {
 	case 0: return gemm_tc_persistent_kernel<0, false, TWO_SM>;
 	case 1: return gemm_tc_persistent_kernel<0, true, TWO_SM>;
@@ -1189,7 +1203,11 @@ static void persistent_attrs_once()
 		gemm_tc_persistent_kernel<3, false, false>,
 		gemm_tc_persistent_kernel<0, false, true>, gemm_tc_persistent_kernel<0, true, true>, gemm_tc_persistent_kernel<1, false, true>,
 		gemm_tc_persistent_kernel<1, true, true>, gemm_tc_persistent_kernel<2, false, true>, gemm_tc_persistent_kernel<2, true, true>,
-		gemm_tc_persistent_kernel<3, false, true> };
+		gemm_tc_persistent_kernel<3, false, true>,
+		gemm_tc_persistent_kernel<0, false, false, true>, gemm_tc_persistent_kernel<0, true, false, true>, gemm_tc_persistent_kernel<1, false, false, true>,
+		gemm_tc_persistent_kernel<1, true, false, true>, gemm_tc_persistent_kernel<2, false, false, true>, gemm_tc_persistent_kernel<2, true, false, true>,
+		gemm_tc_persistent_kernel<0, false, true, true>, gemm_tc_persistent_kernel<0, true, true, true>, gemm_tc_persistent_kernel<1, false, true, true>,
+		gemm_tc_persistent_kernel<1, true, true, true>, gemm_tc_persistent_kernel<2, false, true, true>, gemm_tc_persistent_kernel<2, true, true, true> };
 	for (PersistentKernel k : ks) CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 }
 
