@@ -443,10 +443,13 @@ void k_gemm_simt(cudaStream_t s, const View& c, const View& a, const View& b, bo
 // depend on the order in which blocks arrive, so a GroupNorm (and with it a whole graph run) is bit-reproducible.
 // stats layout: [N][groups][4] 64-bit words = (sum hi, sum lo, sum-of-squares hi, sum-of-squares lo), zeroed before the run.
 constexpr double GN_FIX = 1099511627776.0;      // 2^40
-__device__ __forceinline__ void gn_fix_add(unsigned long long* dst, double v)
+// The value added is one block's share of a group (a few thousand f16 values): f32 holds it to 1e-7 relative and the split of an
+// f32 is exact (its fraction times 2^40 is an integer). FP64 arithmetic and 64-bit float <-> integer conversions are slow on
+// this part (the same split in double cost 12K clk per tile in the GEMM epilogue, profiles/r2_ncu_gemm.md).
+__device__ __forceinline__ void gn_fix_add(unsigned long long* dst, float v)
 {
-	const double hi = floor(v);
-	const long long ihi = (long long)hi, ilo = (long long)((v - hi) * GN_FIX);
+	const float hi = floorf(v);
+	const long long ihi = (long long)hi, ilo = (long long)((v - hi) * 1099511627776.0f);
 	atomicAdd(dst, (unsigned long long)ihi);        // two's complement: negative sums wrap correctly
 	atomicAdd(dst + 1, (unsigned long long)ilo);
 }
@@ -477,8 +480,8 @@ __device__ __forceinline__ void gn_block_finish(const float* su, const float* sq
 	for (int g = threadIdx.x; g < groups; g += blockDim.x) {
 		const int g_lo = max(g * cpg, c_lo), g_hi = min((g + 1) * cpg, c_hi);
 		if (g_lo >= g_hi) continue;
-		double a = 0.0, b = 0.0;
-		for (int c = g_lo; c < g_hi; ++c) { a += (double)chs[(c - c_lo) * 2]; b += (double)chs[(c - c_lo) * 2 + 1]; }
+		float a = 0.f, b = 0.f;
+		for (int c = g_lo; c < g_hi; ++c) { a += chs[(c - c_lo) * 2]; b += chs[(c - c_lo) * 2 + 1]; }
 		unsigned long long* dst = stats + ((size_t)n * groups + g) * 4;
 		gn_fix_add(dst, a); gn_fix_add(dst + 2, b);
 	}
@@ -667,12 +670,34 @@ gn_apply_fast_kernel(const __half* __restrict__ x, __half* __restrict__ y, long 
 	const int ch = slab * slab_chunks + (int)(threadIdx.x % slab_chunks);
 	const int plane = threadIdx.x / slab_chunks, planes = blockDim.x / slab_chunks;
 	if (ch >= chunks) return;
-	float sc[8], sh[8];
+	// scale / shift of my 8 channels: one division (the channels are consecutive: the group index only steps), vector loads of
+	// the affine parameters -- this set-up was 23 % of the kernel's samples with 8 divisions and 16 scalar loads per thread
+	float sc[8], sh[8], ga[8], be[8];
+	#pragma unroll
+	for (int j = 0; j < 8; ++j) { ga[j] = 1.f; be[j] = 0.f; }
+	if (gamma) {
+		if (!((uintptr_t)gamma & 15)) {
+			const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8 + 4));
+			ga[0] = g0.x; ga[1] = g0.y; ga[2] = g0.z; ga[3] = g0.w; ga[4] = g1.x; ga[5] = g1.y; ga[6] = g1.z; ga[7] = g1.w;
+		} else {
+			#pragma unroll
+			for (int j = 0; j < 8; ++j) ga[j] = gamma[ch * 8 + j];
+		}
+		if (beta) {
+			if (!((uintptr_t)beta & 15)) {
+				const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + ch * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + ch * 8 + 4));
+				be[0] = b0.x; be[1] = b0.y; be[2] = b0.z; be[3] = b0.w; be[4] = b1.x; be[5] = b1.y; be[6] = b1.z; be[7] = b1.w;
+			} else {
+				#pragma unroll
+				for (int j = 0; j < 8; ++j) be[j] = beta[ch * 8 + j];
+			}
+		}
+	}
+	int g = (ch * 8) / cpg, rem = ch * 8 - g * cpg;              // channel ch * 8 + j sits in group g at offset rem
 	#pragma unroll
 	for (int j = 0; j < 8; ++j) {
-		const int c = ch * 8 + j, g = c / cpg;
-		const float ga = gamma ? gamma[c] : 1.f, be = (gamma && beta) ? beta[c] : 0.f;
-		sc[j] = sm[groups + g] * ga; sh[j] = be - sm[g] * sc[j];
+		sc[j] = sm[groups + g] * ga[j]; sh[j] = be[j] - sm[g] * sc[j];
+		if (++rem == cpg) { rem = 0; ++g; }
 	}
 	const long long p0 = (long long)tile * pix_per_block, p1 = min(HW, p0 + pix_per_block);
 	const __half* base = x + n * img_stride + ch * 8;
