@@ -733,7 +733,7 @@ gn_small_kernel(const __half* __restrict__ x, __half* __restrict__ y, int HW, in
 	long long img_stride, long long pix_stride, long long oimg_stride, long long opix_stride,
 	const float* __restrict__ gamma, const float* __restrict__ beta, float eps, unsigned c2n_mul)
 {
-	__shared__ double red[8];
+	__shared__ float red[8];        // f32 throughout: the second pass is centred (no cancellation), and FP64 division / square root per thread cost more than the slice
 	const int g = blockIdx.x, n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 	const int c2n = cpg >> 1, total = HW * c2n;                 // half2 units per pixel of this group / in the slice
 	const __half* xb = x + n * img_stride + (long long)g * cpg;
@@ -751,24 +751,24 @@ gn_small_kernel(const __half* __restrict__ x, __half* __restrict__ y, int HW, in
 			sum += f.x + f.y;
 		}
 	}
-	auto block_sum = [&](float s) -> double {
+	auto block_sum = [&](float s) -> float {
 		#pragma unroll
 		for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(~0u, s, o);
 		__syncthreads();                                         // red[] of the previous reduction has been consumed
-		if (lane == 0) red[w] = (double)s;
+		if (lane == 0) red[w] = s;
 		__syncthreads();
-		double t = 0.0;
+		float t = 0.f;
 		#pragma unroll
 		for (int i = 0; i < 8; ++i) t += red[i];
 		return t;
 	};
-	const double cnt = (double)HW * cpg;
-	const float mean = (float)(block_sum(sum) / cnt);
+	const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
+	const float mean = block_sum(sum) * inv_cnt;
 	float sq = 0.f;
 	#pragma unroll
 	for (int i = 0; i < NV; ++i)
 		if (tid + i * 256 < total) { const float2 f = __half22float2(v[i]); const float a = f.x - mean, b = f.y - mean; sq = fmaf(a, a, sq); sq = fmaf(b, b, sq); }
-	const float rstd = (float)(1.0 / sqrt(block_sum(sq) / cnt + (double)eps));
+	const float rstd = rsqrtf(block_sum(sq) * inv_cnt + eps);
 	#pragma unroll
 	for (int i = 0; i < NV; ++i) {
 		const int e = tid + i * 256;
