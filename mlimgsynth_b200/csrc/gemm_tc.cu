@@ -914,6 +914,24 @@ static bool env_on(const char* n, bool dflt) { const char* e = getenv(n); return
 // K = 11520 / 23040): with 40-112 tiles every CTA has to pull 5+ MB of operands through its own L2 port and the launch is
 // ingest-bound at ~590 TFLOP/s. Here 128 x 256 tiles are cut along K so that about one CTA per SM works on 1/S of it,
 // writing f32 partials; a second pass sums them and applies the epilogue.
+static bool persistent_eligible(const GemmParams& p, const GemmEpilogue& ep);
+static int max_active_clusters(int csize, int sm_count);
+// The same few-tile, long-K contractions fit ONE wave of CTA pairs (tcgen05 cta_group::2, 256 x BN per pair) when BN is chosen so that
+// about 3/4 of the pairs get a tile: every SM then pulls its 128 rows of A and only half of a NARROW B tile per k-block, no f32
+// partials and no reduction pass. Measured (run r3j, M = 1024, N = 1280): K = 11520 37.1 us with BN = 96 against 46.0 us for split-K
+// (38.9 us with BN = 128), K = 23040 67.6 us against 71.8 us. Returns the BN to use, 0 if there is no such tiling.
+static int one_wave_pair_bn(const GemmParams& p, const GemmEpilogue& ep, int64_t m_tiles, int sm_count)
+{
+	if (!env_on("GGML_B200_GEMM_2SM", true) || !env_on("GGML_B200_GEMM_PAIRWAVE", true) || m_tiles < 2 || !persistent_eligible(p, ep) || ep.geglu) return 0;
+	const int nclusters = max_active_clusters(2, sm_count);
+	if (nclusters <= 0) return 0;
+	const int64_t m_pairs = (m_tiles + 1) / 2;
+	for (int bn = 96; bn <= 128; bn += 32) {
+		const int64_t n_tiles = (p.N + bn - 1) / bn, ctiles = m_pairs * n_tiles;
+		if (n_tiles >= 2 && ctiles <= nclusters && ctiles * 4 >= (int64_t)nclusters * 2) return bn;
+	}
+	return 0;
+}
 static int choose_split_k(const GemmParams& p, const GemmEpilogue& ep, int64_t m_tiles, int sm_count)
 {
 	if (!env_on("GGML_B200_GEMM_SPLITK", true)) return 1;
@@ -922,6 +940,7 @@ static int choose_split_k(const GemmParams& p, const GemmEpilogue& ep, int64_t m
 	if (ep.bias && ((uintptr_t)ep.bias & 15)) return 1;
 	const int64_t tiles = m_tiles * ((p.N + 255) / 256);
 	if (tiles * 2 > sm_count || p.num_kb < 128) return 1;       // measured: K = 11520 -7 %, K = 23040 -18 %, but K = 5120 +25 % (the partial sums cost more than they save)
+	if (one_wave_pair_bn(p, ep, m_tiles, sm_count)) return 1;    // one wave of CTA pairs beats the split (run r3j)
 	int S = (int)std::min<int64_t>(8, sm_count / tiles);
 	S = std::min(S, p.num_kb / 16);
 	return S >= 2 ? S : 1;
@@ -1024,6 +1043,10 @@ static void finish_setup_persistent(GemmTC* g, const GemmEpilogue& ep, int64_t m
 	GemmParams& p = g->p;
 	p.geglu = ep.geglu ? 1 : 0;
 	TileChoice tc = pick_tiles_persistent(m_tiles, p.N, p.num_kb, sm_count, ep.geglu);
+	{	// few tiles, long K: the one-wave CTA-pair tiling (the cost model above underrates it: it ranks by waves x ingest only)
+		const int64_t tiles256 = m_tiles * ((p.N + 255) / 256);
+		if (tiles256 * 2 <= sm_count && p.num_kb >= 128) { const int bn = one_wave_pair_bn(p, ep, m_tiles, sm_count); if (bn) tc = {bn, 1, 1, 1}; }
+	}
 	if (const char* f = getenv("GGML_B200_GEMM_FORCE")) {      // "bn,cm,cn[,two_sm]": tuning experiments (tools/gemm_bench.py)
 		int bn = 0, cm = 1, cn = 1, two = 0;
 		if (sscanf(f, "%d,%d,%d,%d", &bn, &cm, &cn, &two) >= 3 && bn >= 16 && bn <= 256 && bn % 16 == 0 && bn % (8 * cm) == 0 &&
