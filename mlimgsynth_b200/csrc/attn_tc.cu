@@ -1489,7 +1489,7 @@ attn_ap_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 //   warps 0..3 / 4..7  slot a / b: one query row per thread -- maximum, exponentials, P (f16, over the consumed scores),
 //           then O / l -> f16 -> global memory, and the slot's accumulator is handed back (o_free).
 template <int D16MAX>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(320, D16MAX <= 64 ? 2 : 1)
 attn_kv1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
 	const AttnParams p)
 {
@@ -1513,7 +1513,12 @@ attn_kv1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 	const int h = blockIdx.y, b = blockIdx.z;
 	const int n_tiles = (p.nq + AQ - 1) / AQ;
 	const int n_my = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;   // tiles blockIdx.x, + gridDim.x, ...
-	constexpr uint32_t O_BASE = 256, O_STRIDE = 128;      // TMEM: S_t at t*128 (P_t over its first columns), O_t at 256 + t*128
+	// TMEM: S_t at t*128 (P_t over its first columns), O_t at 256 + t*128. COMPACT (the 77-token context with heads up to 48 wide:
+	// SD1.x level 0): scores 80 + output 48 columns fit one 128-column slot, the CTA allocates 256 columns and TWO CTAs share an SM --
+	// the kernel is a latency chain per tile (load, QK^T, softmax, PV, store), so twice the tiles in flight is what it needs
+	const int nk16 = (p.nk + 15) & ~15;                   // keys the products cover (rows past nk are zero-filled by TMA)
+	const bool compact = D16MAX <= 64 && nk16 <= 80 && p.d16 <= 48;
+	const uint32_t O_BASE = compact ? 80u : 256u, O_STRIDE = 128, tmem_cols = compact ? 256u : (uint32_t)A_TMEM_COLS;
 
 	if (threadIdx.x == 0) {
 		tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -1522,12 +1527,11 @@ attn_kv1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 			mbar_init(&pv_full[t], 1); mbar_init(&o_free[t], 4); }
 		fence_barrier_init();
 	}
-	if (warp == 9) tmem_alloc(tmem_slot, A_TMEM_COLS);
+	if (warp == 9) tmem_alloc(tmem_slot, tmem_cols);
 	tc_fence_before();
 	__syncthreads();
 	tc_fence_after();
 	const uint32_t tmem_base = uniform_u32(*tmem_slot);
-	const int nk16 = (p.nk + 15) & ~15;                   // keys the products cover (rows past nk are zero-filled by TMA)
 
 	if (warp == 8) {
 		if (lane == 0 && n_my > 0) {
@@ -1669,7 +1673,7 @@ attn_kv1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 	}
 	tc_fence_before();
 	__syncthreads();
-	if (warp == 9) { tc_fence_after(); tmem_dealloc(tmem_base, A_TMEM_COLS); }
+	if (warp == 9) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
 }
 
 // ------------------------------------------------------------------ host
@@ -1767,7 +1771,8 @@ AttnTC* attn_tc_prepare(const View& o, const View& q, const View& k, const View&
 		if (p.nblk == 1 && p.d16 <= 128 && !(e && atoi(e) == 0)) {
 			const int n_tiles = (p.nq + AQ - 1) / AQ;
 			const long long hb = (long long)p.H * p.B;
-			int x = (int)std::max<long long>(1, 148 / std::max<long long>(1, hb));
+			const bool compact = p.d16 <= 48 && ((p.nk + 15) & ~15) <= 80;         // two CTAs per SM (256 tensor-memory columns each)
+			int x = (int)std::max<long long>(1, (compact ? 296 : 148) / std::max<long long>(1, hb));
 			x = std::min(x, n_tiles);
 			a->kv1 = true;
 			a->grid = dim3((unsigned)x, (unsigned)p.H, (unsigned)p.B);
