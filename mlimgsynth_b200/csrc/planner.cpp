@@ -900,8 +900,10 @@ void Builder::plan_node(ggml_tensor* t)
 			for (int i = (int)P->steps.size() - 1; i >= 0; --i) {
 				const Step& ps = P->steps[i];
 				if (ps.out.buf != a.buf) continue;
+				// (a launch serves ONE group_norm: a second consumer of the same tensor keeps its own statistics pass and slot -- if
+				// the producer turns out not to fuse at run time, two passes adding into one slot would count every element twice)
 				bool same = (ps.kind == S_GEMM_TC || ps.kind == S_CONV_TC) && ps.out.dt == DT_F16 && ps.out.off == a.off && ps.out.numel() == a.numel() &&
-					!(ps.kind == S_GEMM_TC && (ps.iparam[0] == 1 || ps.ldc != ps.N)) && ps.N == a.ne[2] && (ps.gn_groups == 0 || ps.gn_groups == groups);
+					!(ps.kind == S_GEMM_TC && (ps.iparam[0] == 1 || ps.ldc != ps.N)) && ps.N == a.ne[2] && ps.gn_groups == 0;
 				if (same) producer = i;
 				break;
 			}
@@ -910,12 +912,9 @@ void Builder::plan_node(ggml_tensor* t)
 		s.out = o; s.in[0] = a; s.n_in = 1; s.fparam = eps; s.iparam[0] = groups; s.iparam[1] = silu ? 1 : 0;
 		if (has_w) { s.bias = gw; s.has_bias = true; }
 		if (has_b) { s.rowvec = gb; s.has_rowvec = true; }
-		if (producer >= 0 && P->steps[producer].gn_groups == groups) s.stats_off = P->steps[producer].stats_off;      // a second consumer of the same statistics
-		else {
-			s.stats_off = P->zero_bytes;
-			P->zero_bytes += (size_t)4 * groups * t->ne[3] * sizeof(unsigned long long);     // fixed-point (hi, lo) sum and sum of squares
-			if (producer >= 0) { Step& ps = P->steps[producer]; ps.gn_groups = groups; ps.stats_off = s.stats_off; ps.gn_rows_per_image = a.ne[0] * a.ne[1]; }
-		}
+		s.stats_off = P->zero_bytes;
+		P->zero_bytes += (size_t)4 * groups * t->ne[3] * sizeof(unsigned long long);     // fixed-point (hi, lo) sum and sum of squares
+		if (producer >= 0) { Step& ps = P->steps[producer]; ps.gn_groups = groups; ps.stats_off = s.stats_off; ps.gn_rows_per_image = a.ne[0] * a.ne[1]; }
 		s.gn_producer = producer;
 		done[t] = true;
 		finish(last, o);
