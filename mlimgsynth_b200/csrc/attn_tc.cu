@@ -18,6 +18,11 @@
 //                 tcgen05.st; the PV tile of the previous block is folded into the register
 //                 accumulator with the online-softmax correction while the tensor core is busy.
 // Head dims 40 / 80 (SD1.x) are handled by TMA zero-fill up to the next multiple of 16.
+// Kernels in this file, by head width and context length (attn_tc_launch picks; every variant is selectable by environment):
+//   attn_ap_kernel     heads <= 48 wide, more than one key block: two query tiles per CTA, scores three blocks deep (SD1.x level 0)
+//   attn_split_kernel  heads 49..64 wide: key halves, eight softmax warps per tile, two CTAs per SM (SDXL, SD2.x)
+//   attn_tc_kernel     wider heads (80, 160) and the round-1 forms; attn_split4_kernel: measured-slower variants kept for reference
+//   attn_kv1_kernel    one key block (the 77-token text context): a CTA walks the query tiles of its (head, image)
 // Roofline: tensor (4*nq*nk*d FLOP per head); for d <= 64 the MUFU.EX2 rate (16/clk/SM) is the
 // practical limit (1024 clk per 128x128 tile vs 2*(d/16)*64 clk of MMA).
 #include "kernels.h"
