@@ -78,6 +78,9 @@ GemmTC* gemm_tc_prepare(const __half* A, int64_t lda, const __half* B, int64_t l
 // 3x3 stride-1 pad-1 convolution on channels-last x[N,H,W,Cin] (f16), weights [Cout][9*Cin] prepared.
 GemmTC* conv3x3_tc_prepare(const __half* x, int64_t n_img, int64_t H, int64_t W, int64_t Cin,
 	const __half* Wt, void* C, DT c_dt, int64_t Cout, const GemmEpilogue& ep, int sm_count);
+// direct 3x3 s1 p1 convolution for 3 / 4 output channels (UNet conv_out, last VAE convolution): f16 NHWC in and out, bias only
+bool k_conv3x3_small_supported(int64_t Cin, int64_t Cout);
+void k_conv3x3_small(cudaStream_t s, __half* y, const __half* x, const __half* w, const float* bias, int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout);
 void gemm_tc_launch(cudaStream_t s, GemmTC* g);
 bool gemm_tc_gn_fused(const GemmTC* g);   // the launch adds the GroupNorm statistics of its output to ep.gn_stats
 void gemm_tc_free(GemmTC* g);

@@ -1272,4 +1272,114 @@ void k_conv_weight_prep(cudaStream_t s, __half* dst, int64_t kpad, const View& w
 	g_stats.kernel_launches++;
 }
 
+// ------------------------------------------------------------------ 3x3 convolution with 3 or 4 output channels (direct, SIMT)
+// conv_out of the UNet (320 -> 4, unet.c:338) and the last convolution of the VAE decoder (128 -> 3, vae.c:262) are the two
+// launches the tensor-core path cannot serve: a 128 x 16 MMA tile wastes 3/4 of its columns and the 4- / 3-channel output row
+// is too narrow for the TMA store, so they ran on the non-persistent kernel at 7-18 TFLOP/s (81 us and 1035 us). Here a block
+// owns 32 x 8 output pixels (one per thread): the input halo (34 x 10 pixels) goes through shared memory in chunks of 64
+// channels (pixel pitch 144 B: the 16-byte loads of a quarter-warp fall on 32 different banks), the weights of the chunk sit
+// beside it in f32 and are read as warp-wide broadcasts, the products accumulate in f32 pairs (FFMA2).
+__device__ __forceinline__ unsigned long long f2_pack(float a, float b) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c)
+{ unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+constexpr int CS_TW = 32, CS_TH = 8, CS_CC = 64, CS_PITCH = CS_CC * 2 + 16, CS_HALO = (CS_TW + 2) * (CS_TH + 2);
+template <int COUT>
+__global__ void __launch_bounds__(256, 3)
+conv3x3_small_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias, __half* __restrict__ y,
+	int H, int W, int Cin, int tiles_w, int tiles_h)
+{
+	extern __shared__ __align__(16) uint8_t cs_sm[];
+	uint8_t* sx = cs_sm;                                            // [CS_HALO pixels][CS_PITCH bytes]
+	float* sw = reinterpret_cast<float*>(cs_sm + CS_HALO * CS_PITCH);   // [COUT][9][CS_CC]
+	const int tid = threadIdx.x, px = tid & 31, py = tid >> 5;
+	int b = blockIdx.x;
+	const int tx = b % tiles_w; b /= tiles_w;
+	const int ty = b % tiles_h; const int n = b / tiles_h;
+	const int x0 = tx * CS_TW, y0 = ty * CS_TH;
+	const __half* xin = x + (long long)n * H * W * Cin;
+	unsigned long long acc[COUT];
+	#pragma unroll
+	for (int co = 0; co < COUT; ++co) acc[co] = 0ull;
+	for (int c0 = 0; c0 < Cin; c0 += CS_CC) {
+		__syncthreads();                                            // the previous chunk has been consumed
+		for (int idx = tid; idx < CS_HALO * 8; idx += 256) {
+			const int pix = idx >> 3, part = idx & 7;
+			const int gy = y0 - 1 + pix / (CS_TW + 2), gx = x0 - 1 + pix % (CS_TW + 2);
+			uint4 v = make_uint4(0u, 0u, 0u, 0u);                   // zero padding outside the image
+			if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(reinterpret_cast<const uint4*>(xin + ((long long)gy * W + gx) * Cin + c0 + part * 8));
+			*reinterpret_cast<uint4*>(sx + pix * CS_PITCH + part * 16) = v;
+		}
+		for (int idx = tid; idx < COUT * 9 * CS_CC; idx += 256) {
+			const int co = idx / (9 * CS_CC), r = idx - co * 9 * CS_CC, tap = r / CS_CC, c = r - tap * CS_CC;
+			sw[idx] = __half2float(w[(long long)co * 9 * Cin + (long long)tap * Cin + c0 + c]);
+		}
+		__syncthreads();
+		#pragma unroll
+		for (int tap = 0; tap < 9; ++tap) {
+			const uint8_t* p = sx + ((py + tap / 3) * (CS_TW + 2) + px + tap % 3) * CS_PITCH;
+			#pragma unroll 2
+			for (int part = 0; part < 8; ++part) {
+				const uint4 raw = *reinterpret_cast<const uint4*>(p + part * 16);
+				const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+				unsigned long long f[4];
+				#pragma unroll
+				for (int j = 0; j < 4; ++j) { const float2 t = __half22float2(h2[j]); f[j] = f2_pack(t.x, t.y); }
+				#pragma unroll
+				for (int co = 0; co < COUT; ++co) {
+					const float4* wp = reinterpret_cast<const float4*>(sw + (co * 9 + tap) * CS_CC + part * 8);
+					const float4 w0 = wp[0], w1 = wp[1];
+					acc[co] = f2_fma(f[0], f2_pack(w0.x, w0.y), acc[co]);
+					acc[co] = f2_fma(f[1], f2_pack(w0.z, w0.w), acc[co]);
+					acc[co] = f2_fma(f[2], f2_pack(w1.x, w1.y), acc[co]);
+					acc[co] = f2_fma(f[3], f2_pack(w1.z, w1.w), acc[co]);
+				}
+			}
+		}
+	}
+	const int gx = x0 + px, gy = y0 + py;
+	if (gx < W && gy < H) {
+		__half* o = y + (((long long)n * H + gy) * W + gx) * COUT;
+		float r[COUT];
+		#pragma unroll
+		for (int co = 0; co < COUT; ++co) {
+			float a, c; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(c) : "l"(acc[co]));
+			r[co] = a + c + (bias ? bias[co] : 0.f);
+		}
+		if (COUT == 4) {
+			uint2 pk; __half2* hp = reinterpret_cast<__half2*>(&pk);
+			hp[0] = __floats2half2_rn(r[0], r[1]); hp[1] = __floats2half2_rn(r[2], r[3 % COUT]);
+			*reinterpret_cast<uint2*>(o) = pk;
+		} else {
+			#pragma unroll
+			for (int co = 0; co < COUT; ++co) o[co] = __float2half_rn(r[co]);
+		}
+	}
+}
+
+bool k_conv3x3_small_supported(int64_t Cin, int64_t Cout)
+{
+	// opt-in (GGML_B200_CONV_SMALL=1): parity-green on hardware (tests/test_ops_gpu.py::test_conv3x3_small_direct, 3e-4 vs the oracle)
+	// but measured at 89 us on the UNet's conv_out (64 x 64 x 320 -> 4, 16 latents: 256 blocks of 8 warps leave the chip latency-bound),
+	// no better than the tensor-core fallback; it needs pixel tiles of 16 x 8 and a double-buffered halo before it becomes the default
+	const char* e = getenv("GGML_B200_CONV_SMALL");              // read per plan (a test switches it inside one process)
+	const bool on = e && atoi(e) != 0;
+	return on && (Cout == 3 || Cout == 4) && Cin % CS_CC == 0;
+}
+// x: [N][H][W][Cin] f16 dense, w: [Cout][9 * Cin] f16 (kh, kw, Cin order: k_conv_weight_prep), y: [N][H][W][Cout] f16 dense
+void k_conv3x3_small(cudaStream_t s, __half* y, const __half* x, const __half* w, const float* bias, int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout)
+{
+	const int tiles_w = (int)((W + CS_TW - 1) / CS_TW), tiles_h = (int)((H + CS_TH - 1) / CS_TH);
+	const unsigned grid = (unsigned)(N * tiles_h * tiles_w);
+	const size_t smem = (size_t)CS_HALO * CS_PITCH + (size_t)Cout * 9 * CS_CC * sizeof(float);
+	static bool attr = false;
+	if (!attr) {
+		CUDA_CHECK(cudaFuncSetAttribute(conv3x3_small_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+		CUDA_CHECK(cudaFuncSetAttribute(conv3x3_small_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+		attr = true;
+	}
+	if (Cout == 4) conv3x3_small_kernel<4><<<grid, 256, smem, s>>>(x, w, bias, y, (int)H, (int)W, (int)Cin, tiles_w, tiles_h);
+	else conv3x3_small_kernel<3><<<grid, 256, smem, s>>>(x, w, bias, y, (int)H, (int)W, (int)Cin, tiles_w, tiles_h);
+	g_stats.kernel_launches++;
+}
+
 }  // namespace b200

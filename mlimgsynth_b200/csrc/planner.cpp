@@ -1170,6 +1170,12 @@ static void run_step(Plan* P, Step& s, cudaStream_t st)
 		else k_attention(st, o, q, k, v, s.fparam, s.iparam[0] != 0);
 	} break;
 	case S_GEMM_TC: case S_CONV_TC: {
+		if (s.kind == S_CONV_TC && !s.tc && !s.has_rowvec && !s.has_residual && s.act == U_NONE && s.out.dt == DT_F16 && s.gn_groups == 0 &&
+			k_conv3x3_small_supported(s.conv_c, s.N)) {          // 3 / 4 output channels: direct kernel (conv_out, last VAE convolution)
+			k_conv3x3_small(st, (__half*)buf_ptr(P, s.out), (const __half*)buf_ptr(P, s.in[0]), (const __half*)buf_ptr(P, s.in[1]),
+				s.has_bias ? (const float*)buf_ptr(P, s.bias) : nullptr, s.conv_n, s.conv_h, s.conv_w, s.conv_c, s.N);
+			break;
+		}
 		if (!s.tc) {
 			GemmEpilogue ep;
 			if (s.has_bias) ep.bias = (const float*)buf_ptr(P, s.bias);

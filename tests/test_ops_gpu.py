@@ -349,3 +349,40 @@ def test_groupnorm_stats_from_epilogue_blocks(ref, eng, monkeypatch):
     for x in (fused, pair, plain):
         assert max_rel_err(x, r) <= BLOCK_TOL
     assert max_rel_err(fused, plain) <= 2e-3 and max_rel_err(pair, plain) <= 2e-3
+
+
+# ---------------------------------------------------------------- direct kernel for 3 / 4 output channels (opt-in)
+# conv3x3_small_kernel (UNet conv_out, last VAE convolution): opt-in (GGML_B200_CONV_SMALL=1), correct on hardware (3e-4 vs the
+# oracle, like the tensor-core path) but not faster on the UNet shape (89 us for 64 x 64 x 320 -> 4 x 16 latents: only 256 blocks),
+# so it stays off by default. Run in a SUBPROCESS so that an experimental kernel can never disturb the CUDA context of the suite.
+_SMALL_CONV_SCRIPT = r"""
+import json, os, sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
+import numpy as np
+import mlimgsynth_b200
+from mlimgsynth_b200.ggml import GGML
+from blocks import run_both, max_rel_err
+eng = mlimgsynth_b200.load_engine(); eng.init_backend()
+ref = GGML(os.path.join(%(root)r, "oracle", "_ref", "libggml_ref.so"))
+out = []
+for (W, H, Cin, Cout, N) in [(64, 64, 320, 4, 2), (16, 16, 128, 3, 1), (35, 10, 128, 3, 2), (33, 9, 64, 4, 1)]:
+    build = lambda b: b.conv2d(b.inp(N, Cin, H, W), Cout)
+    os.environ["GGML_B200_CONV_SMALL"] = "0"
+    (r,), (tc,) = run_both(build, ref, eng, 9)
+    os.environ["GGML_B200_CONV_SMALL"] = "1"
+    (_,), (direct,) = run_both(build, ref, eng, 9)
+    out.append([bool(np.isfinite(direct).all()), max_rel_err(direct, r), max_rel_err(direct, tc), max_rel_err(tc, r)])
+print("RESULT " + json.dumps(out))
+"""
+
+
+def test_conv3x3_small_direct():
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", _SMALL_CONV_SCRIPT % {"root": root}], env=dict(os.environ, GGML_B200_QUIET="1"),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-1500:]
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    print("direct 3x3 convolution, 3 / 4 output channels: (finite, vs oracle, vs tensor-core path, tensor-core vs oracle)", res)
+    for finite, e_ref, e_tc, _ in res:
+        assert finite and e_ref <= OP_TOL and e_tc <= OP_TOL

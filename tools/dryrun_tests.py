@@ -20,7 +20,7 @@ for name, fn in inspect.getmembers(T, inspect.isfunction):
     if marks:
         cases = [c if isinstance(c, tuple) else (c,) for c in marks[0].args[1]]
     for c in cases:
-        if name in ("test_multi_compute_and_reupload",) or "monkeypatch" in inspect.signature(fn).parameters:
+        if name in ("test_multi_compute_and_reupload", "test_conv3x3_small_direct") or "monkeypatch" in inspect.signature(fn).parameters:
             continue
         print(name, c, flush=True)
         fn(eng, eng, *c); n += 1
