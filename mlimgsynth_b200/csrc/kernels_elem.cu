@@ -1360,7 +1360,8 @@ bool k_conv3x3_small_supported(int64_t Cin, int64_t Cout)
 {
 	// opt-in (GGML_B200_CONV_SMALL=1): parity-green on hardware (tests/test_ops_gpu.py::test_conv3x3_small_direct, 3e-4 vs the oracle)
 	// but measured at 89 us on the UNet's conv_out (64 x 64 x 320 -> 4, 16 latents: 256 blocks of 8 warps leave the chip latency-bound),
-	// no better than the tensor-core fallback; it needs pixel tiles of 16 x 8 and a double-buffered halo before it becomes the default
+	// no better than the tensor-core fallback there (the VAE's last convolution, 512 x 512 x 128 -> 3 x 8 images, runs at 623 us against
+	// 1021 us); it needs smaller pixel tiles and a double-buffered halo before it becomes the default
 	const char* e = getenv("GGML_B200_CONV_SMALL");              // read per plan (a test switches it inside one process)
 	const bool on = e && atoi(e) != 0;
 	return on && (Cout == 3 || Cout == 4) && Cin % CS_CC == 0;
